@@ -1,0 +1,87 @@
+"""Community bookkeeping behind the reference's ``Pathways`` interface (``pathways.py:8-429``).
+
+Name resolution stays on the host exactly as in the reference (numpy string ``intersect1d``;
+SURVEY.md 8f-1 lists the integer-id fast path as the next widening step); the community-level
+random masks live in ``masks.py`` (device), and ``aggregate`` runs the segmented-mean kernel.
+"""
+import itertools
+
+import numpy as np
+import pandas as pd
+import torch
+
+from . import _lib
+from .engine import require_cuda
+
+
+class Pathways:
+    def __init__(self, communities, community_names, community_types=None):
+        self.communities = communities
+        self.community_names = community_names
+        self.community_types = community_types
+        if self.community_names is None:
+            self.community_names = np.arange(len(self.communities)).tolist()
+
+    def comp_graph(self, names):
+        """pathways.py:33-102: keep communities with at least one member in the subgraph."""
+        names_array = np.array(names, dtype=str)
+        sub, sub_names = [], []
+        sub_types = [] if self.community_types is not None else None
+        for i, (community, cname) in enumerate(zip(self.communities, self.community_names)):
+            common = np.intersect1d(np.array(community, dtype=str), names_array)
+            if len(common) > 0:
+                sub.append(common.tolist())
+                sub_names.append(cname)
+                if sub_types is not None:
+                    sub_types.append(self.community_types[i])
+        if sub_types is not None:
+            sub_types = torch.tensor(sub_types, device=self.community_types.device)
+        return sub, sub_names, sub_types
+
+    def names2inds(self, names):
+        """pathways.py:104-136: member names -> subgraph indices, in lexicographic name order."""
+        if isinstance(self.communities[0][0], int):
+            return self.communities
+        names_array = np.array(names, dtype=str)
+        inds = []
+        for community in self.communities:
+            _, ind, _ = np.intersect1d(names_array, np.array(community, dtype=str), return_indices=True)
+            inds.append(ind.tolist())
+        return inds
+
+    def shift_hetero_pathways(self, pointers):
+        for key, pointer in zip(list(self.communities.keys()), pointers):
+            for i in range(len(self.communities[key])):
+                self.communities[key][i] = (np.array(self.communities[key][i]) + pointer).tolist()
+
+    def hetero2homo(self, problem, node_pointers=None, edge_pointers=None):
+        """pathways.py:162-232 (note the exact ``problem == "node"`` match of :210-213)."""
+        if not isinstance(self.communities, dict):
+            return self.communities, self.community_names, None
+        keys = list(self.communities.keys())
+        first = self.communities[keys[0]][0][0]
+        if isinstance(first, (int, float)):
+            if problem == "node":
+                self.shift_hetero_pathways(node_pointers)
+            elif problem == "edge":
+                self.shift_hetero_pathways(edge_pointers)
+        types, homo, homo_names = [], [], []
+        for i, key in enumerate(keys):
+            types.append(torch.zeros(len(self.communities[key])) + i)
+            homo.extend(self.communities[key])
+            homo_names.append(self.community_names[key])
+        return homo, list(itertools.chain.from_iterable(homo_names)), torch.hstack(types)
+
+    def aggregate(self, config_val, community_inds):
+        """pathways.py:387-429: mean importance per community (device), sorted DataFrame."""
+        lib = _lib.load()
+        dev = require_cuda()
+        w = config_val.detach().to(dev, torch.float32).contiguous()
+        lens = [len(c) for c in community_inds]
+        ptr = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int32, device=dev)
+        idx = torch.tensor(list(itertools.chain.from_iterable(community_inds)) or [0], dtype=torch.int32, device=dev)
+        score = torch.empty(max(len(lens), 1), dtype=torch.float32, device=dev)
+        _lib.check(lib.xpgnn_community_mean(w.data_ptr(), ptr.data_ptr(), idx.data_ptr(), len(lens), score.data_ptr(),
+                                            _lib.stream_ptr()))
+        df = pd.DataFrame({"name": self.community_names, "score": score[:len(lens)].cpu().tolist()}).set_index("name")
+        return df.sort_values(by=["score"], ascending=False).dropna()

@@ -117,3 +117,17 @@ class HomoSAGE(nn.Module):
         for l in self.fc:
             x = l(x)
         return x
+
+
+def build_model(spec, state=None):
+    spec = dict(spec)
+    cls = globals()[spec.pop("cls")]
+    if "relations" in spec:
+        spec["relations"] = [tuple(r) for r in spec["relations"]]
+    for k in ("conv_dims", "head_dims"):
+        if k in spec:
+            spec[k] = tuple(spec[k])
+    m = cls(**spec)
+    if state is not None:
+        m.load_state_dict(state)
+    return m.eval()

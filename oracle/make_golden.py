@@ -148,18 +148,7 @@ def build_cases():
     return cases
 
 
-def build_model(spec, state=None):
-    spec = dict(spec)
-    cls = getattr(fm, spec.pop("cls"))
-    if "relations" in spec:
-        spec["relations"] = [tuple(r) for r in spec["relations"]]
-    for k in ("conv_dims", "head_dims"):
-        if k in spec:
-            spec[k] = tuple(spec[k])
-    m = cls(**spec)
-    if state is not None:
-        m.load_state_dict(state)
-    return m.eval()
+build_model = fm.build_model
 
 
 # ----------------------------------------------------------------------------- run + compare

@@ -1,0 +1,268 @@
+"""GPU parity tests: CUDA path (through the C ABI) vs the reference goldens and the oracle.
+
+Bars (BASELINE.json north_star): coalition masks and k-hop indices bit-exact; perturbed
+predictions within 1e-4 relative (fp32); importances within 1e-3 with identical community ranking.
+"""
+import copy
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import golden_io as gio
+
+pytestmark = pytest.mark.gpu
+
+Y_RTOL, Y_ATOL = 1e-4, 1e-6      # perturbed predictions (fp32 path)
+W_TOL = 1e-3                      # importances / community scores
+
+
+def _run_product(case, prune):
+    from bikg_graph_explainability_public_b200 import Explainer
+
+    meta = case["meta"]
+    names, pathways, pnames = gio.fresh_inputs(case)
+    if meta["hetero"]:
+        feat = {k: v.clone() for k, v in case["feat"].items()}
+        ei = {k: v.clone() for k, v in case["edge_index"].items()}
+    else:
+        feat, ei = case["feat"].clone(), case["edge_index"].clone()
+    arch = gio.build_arch(case)
+    if "rng_state" in case["z"].files:
+        torch.set_rng_state(torch.from_numpy(case["z"]["rng_state"].copy()))
+    ex = Explainer(feat, ei, arch, dict(meta["params"]), names, pathways, pnames, meta["element_type"], meta["problem"])
+    ex.options = dict(prune=prune)
+    cfg, pdf = ex.run(meta["element"], meta["times"])
+    return ex, cfg, pdf
+
+
+@pytest.mark.parametrize("prune", [False, True])
+@pytest.mark.parametrize("name", gio.CASES)
+def test_explainer_matches_reference_golden(name, prune):
+    case = gio.load_case(name)
+    z, meta = case["z"], case["meta"]
+    ex, cfg, pdf = _run_product(case, prune)
+    last = ex._last
+    r = meta["times"] - 1  # intermediates of the last repeat are kept
+
+    # k-hop subgraph: bit exact
+    assert np.array_equal(last["sub_edge_index"].cpu().numpy(), z["sub_edge_index"])
+    assert last["sub_ind"] == int(z["sub_ind"])
+    # coalition masks: bit exact, incl. the shuffle and the row -> community map
+    co = last["coalitions"]
+    gm = gio.golden_mask(case, r)
+    assert co.n_coalitions == gm.shape[0] and co.batch_size == int(z["batch_size_%d" % r])
+    assert np.array_equal(co.dense().cpu().numpy(), gm)
+    if "pathway_rows_%d" % r in z.files:
+        assert np.array_equal(co.pathway_rows.cpu().numpy(), z["pathway_rows_%d" % r])
+    assert np.array_equal(co.popcount.cpu().numpy(), gm.sum(1))
+    # surrogate init continues the same CPU stream: bit exact
+    assert np.array_equal(last["w0"].cpu().numpy(), z["w0_%d" % r])
+    # SHAP kernel weights: float64, same operation order -> exact
+    assert np.array_equal(last["kernel"].cpu().numpy(), z["kernel_%d" % r])
+    # perturbed predictions
+    y_ref = z["y_%d" % r].reshape(-1)
+    np.testing.assert_allclose(last["y"].cpu().numpy(), y_ref, rtol=Y_RTOL, atol=Y_ATOL)
+    # importances, ranking
+    ref_mean = dict(zip([str(x) for x in z["cfg_names"]], z["cfg_mean"]))
+    got = np.array([ref_mean[str(k)] for k in cfg.index])
+    np.testing.assert_allclose(cfg["config_value_mean"].values, got, atol=W_TOL, rtol=W_TOL)
+    ref_std = dict(zip([str(x) for x in z["cfg_names"]], z["cfg_std"]))
+    np.testing.assert_allclose(cfg["config_value_std"].values, np.array([ref_std[str(k)] for k in cfg.index]),
+                               atol=W_TOL, rtol=W_TOL)
+    if "pw_names" in z.files:
+        assert [str(x) for x in pdf.index] == [str(x) for x in z["pw_names"]], "community ranking differs"
+        np.testing.assert_allclose(pdf["score"].values, z["pw_score"], atol=W_TOL, rtol=W_TOL)
+    else:
+        assert pdf is None
+
+
+def test_mask_stream_goldens():
+    """Reference ``Mask`` outputs on shapes the end-to-end cases do not reach: N > 4000 truncation,
+    capped rows, dead-mask repair (C = 2, 3).  SHA-256 of the bool matrix must match."""
+    from bikg_graph_explainability_public_b200.masks import generate_coalitions
+
+    with open(os.path.join(gio.GOLDEN, "mask_stream.json")) as f:
+        specs = json.load(f)
+    for sp in specs:
+        params = dict(interpret_samples=sp["interpret_samples"], epochs=sp["epochs"])
+        torch.manual_seed(sp["seed"] + 2)
+        co = generate_coalitions(sp["n"], copy.deepcopy(sp["communities"]), params)
+        m = co.dense().cpu().numpy()
+        assert m.shape[0] == sp["rows"] and co.batch_size == sp["batch_size"], sp["name"]
+        assert hashlib.sha256(np.ascontiguousarray(m).tobytes()).hexdigest() == sp["sha256_mask"], sp["name"]
+        assert hashlib.sha256(co.pathway_rows.cpu().numpy().astype(np.int32).tobytes()).hexdigest() == sp["sha256_rows"]
+        # the CPU generator must have advanced by exactly the draws the reference consumed
+        from oracle.mt19937 import MT19937
+
+        mt = MT19937(sp["seed"] + 2)
+        mt.raw(sp["consumed"])
+        now = torch.get_rng_state().numpy()
+        assert np.array_equal(mt.to_torch_state(now), now), sp["name"]
+
+
+def test_shap_kernel_goldens():
+    from bikg_graph_explainability_public_b200.kernels import Kernel
+
+    z = np.load(os.path.join(gio.GOLDEN, "shap_kernel.npz"))
+    for key in [k[len("kernel_"):] for k in z.files if k.startswith("kernel_")]:
+        rows, n = (int(v) for v in z["shape_" + key])
+        m = np.unpackbits(z["mask_" + key], axis=1)[:, :n].astype(bool)
+        k = Kernel(torch.from_numpy(m)).compute().cpu().numpy()
+        assert np.array_equal(k, z["kernel_" + key]), key
+
+
+def test_mt19937_stream_matches_torch():
+    from bikg_graph_explainability_public_b200.rng import DeviceStream
+
+    for seed, n in ((0, 5), (7, 624), (11, 625), (123, 100000), (2 ** 31 + 5, 3000)):
+        torch.manual_seed(seed)
+        torch.rand(seed % 17)  # arbitrary position inside the state block
+        st = DeviceStream(torch.device("cuda"))
+        d = st.draw(n)[:n].cpu().numpy().view(np.uint32)
+        ref = torch.randint(0, 2, (n,), dtype=torch.bool).numpy()
+        assert np.array_equal((d & 1).astype(bool), ref)
+        st.hand_back()
+        a = torch.randint(0, 2 ** 31 - 1, (97,))
+        torch.manual_seed(seed)
+        torch.rand(seed % 17)
+        torch.randint(0, 2, (n,), dtype=torch.bool)
+        assert torch.equal(a, torch.randint(0, 2 ** 31 - 1, (97,)))
+
+
+def test_randperm_matches_torch(lib):
+    from bikg_graph_explainability_public_b200 import _lib
+    from bikg_graph_explainability_public_b200.rng import DeviceStream
+
+    for n in (1, 2, 3, 1002, 50000, 60000):  # 60000 > shared-memory capacity -> global path
+        torch.manual_seed(n)
+        st = DeviceStream(torch.device("cuda"))
+        d = st.draw(max(n - 1, 1))
+        perm = torch.empty(n, dtype=torch.int32, device="cuda")
+        _lib.check(lib.xpgnn_randperm(d.data_ptr(), n, perm.data_ptr(), _lib.stream_ptr()))
+        assert torch.equal(perm.cpu().long(), torch.randperm(n))
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_khop_matches_oracle(seed):
+    from bikg_graph_explainability_public_b200.data import khop_subgraph
+    from oracle.xpgnn_oracle import k_hop_subgraph
+
+    g = torch.Generator().manual_seed(seed)
+    n, e = 5000, 20000
+    ei = torch.randint(0, n, (2, e), generator=g)
+    ei[:, :50] = ei[:, 50:100]            # duplicates
+    ei[1, 100:130] = ei[0, 100:130]       # self loops
+    for hops in (0, 1, 2, 3):
+        q = int(torch.randint(0, n, (1,), generator=g))
+        subset, sub_ei, sub_ind, mask, hop, _ = khop_subgraph(ei.cuda(), n, q, hops)
+        s2, e2, i2, m2 = k_hop_subgraph(ei.numpy(), q, hops)
+        assert np.array_equal(subset.cpu().numpy(), s2)
+        assert np.array_equal(sub_ei.cpu().numpy(), e2)
+        assert int(sub_ind) == i2
+        if m2.sum() > 0:
+            assert np.array_equal(mask.cpu().numpy(), m2)
+
+
+def test_khop_isolated_query_gets_self_loop():
+    from bikg_graph_explainability_public_b200.data import khop_subgraph
+
+    ei = torch.tensor([[0, 1], [1, 2]]).cuda()
+    subset, sub_ei, sub_ind, mask, hop, _ = khop_subgraph(ei, 4, 0, 2)  # node 0 has no in-edge
+    assert subset.tolist() == [0] and sub_ei.tolist() == [[0], [0]] and int(sub_ind) == 0
+
+
+def test_csr_is_stable_and_drops_self_loops():
+    from bikg_graph_explainability_public_b200.engine import build_csr
+
+    g = torch.Generator().manual_seed(5)
+    n, e = 300, 4000
+    ei = torch.randint(0, n, (2, e), generator=g)
+    for drop in (False, True):
+        rowptr, col = build_csr(ei[0].cuda(), ei[1].cuda(), n, drop)
+        rowptr, col = rowptr.cpu().numpy(), col.cpu().numpy()
+        src, dst = ei[0].numpy(), ei[1].numpy()
+        keep = (src != dst) if drop else np.ones(e, bool)
+        order = np.argsort(dst[keep], kind="stable")
+        assert rowptr[-1] == keep.sum()
+        assert np.array_equal(col[: rowptr[-1]], src[keep][order])
+        assert np.array_equal(np.diff(rowptr), np.bincount(dst[keep], minlength=n))
+
+
+def _random_model_case(seed, kind, n=400, e=3000, f=20, hidden=(24, 24), s=150):
+    """Engine vs oracle layers on a random multigraph with arbitrary (iid) coalitions."""
+    from oracle import fixture_models as fm
+
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, f, generator=g)
+    ei = torch.randint(0, n, (2, e), generator=g)
+    ei = torch.cat([ei, ei[:, :30], torch.arange(10).repeat(2, 1)], 1)
+    arch = (fm.HomoGCN(f, hidden, (hidden[-1], 8, 1), seed=seed) if kind == "gcn"
+            else fm.HomoSAGE(f, hidden, (hidden[-1], 1), seed=seed)).eval()
+    mask = torch.rand(s, n, generator=g) < 0.5
+    mask[0] = True
+    mask[1] = False
+    q = int(torch.randint(0, n, (1,), generator=g))
+    return x, ei, arch, mask, q
+
+
+@pytest.mark.parametrize("kind", ["gcn", "sage"])
+@pytest.mark.parametrize("seed", [0, 1])
+def test_engine_matches_oracle_on_random_coalitions(kind, seed, lib):
+    from bikg_graph_explainability_public_b200 import _lib
+    from bikg_graph_explainability_public_b200.engine import GraphSpec, MaskedForward
+    from bikg_graph_explainability_public_b200.lowering import lower
+    from oracle.xpgnn_oracle import kernel_output
+
+    x, ei, arch, mask, q = _random_model_case(seed, kind)
+    s, n = mask.shape
+    _, y_ref = kernel_output(mask.numpy(), x, ei.numpy(), arch, q)
+    m8 = mask.to(torch.uint8).cuda().contiguous()
+    w = -(-s // 32)
+    act = torch.zeros((n, w), dtype=torch.int32, device="cuda")
+    pop = torch.zeros(s, dtype=torch.int32, device="cuda")
+    _lib.check(lib.xpgnn_pack_mask(m8.data_ptr(), s, n, act.data_ptr(), w, pop.data_ptr(), _lib.stream_ptr()))
+    assert np.array_equal(pop.cpu().numpy(), mask.sum(1).numpy())
+    eng = MaskedForward(GraphSpec(x.cuda(), ei.cuda(), [0, n]), lower(arch), [q])
+    y = eng(act, s)[:, 0].cpu().numpy()
+    np.testing.assert_allclose(y, y_ref.numpy().reshape(-1), rtol=Y_RTOL, atol=Y_ATOL)
+    # sub-range evaluation (what a rank of a sharded run does) gives the same rows
+    y2 = eng(act, s, 64, 40)[:, 0].cpu().numpy()
+    np.testing.assert_array_equal(y2, y[64:104])
+    # a smaller coalition tile (memory-limited graphs) gives the same numbers
+    eng8 = MaskedForward(GraphSpec(x.cuda(), ei.cuda(), [0, n]), lower(arch), [q], tile_coalitions=8)
+    np.testing.assert_allclose(eng8(act, s)[:, 0].cpu().numpy(), y, rtol=1e-6, atol=1e-7)
+
+
+def test_wlm_fit_matches_closed_form(lib):
+    """Fit kernels vs the oracle's torch-autograd port on random data, both target layouts."""
+    from bikg_graph_explainability_public_b200 import _lib
+    from bikg_graph_explainability_public_b200.masks import CoalitionSet
+    from bikg_graph_explainability_public_b200.wlm import fit_surrogate
+    from oracle.xpgnn_oracle import shap_kernel, train_wlm
+
+    g = torch.Generator().manual_seed(3)
+    params = dict(optimizer="adam", lr=0.01, lr_patience=10, l1_lambda=1e-4)
+    for n, s, b in ((15, 1002, 20), (3000, 257, 33)):
+        mask = torch.rand(s, n, generator=g) < 0.5
+        y = torch.rand(s, generator=g)
+        kern = shap_kernel(mask.numpy())
+        w0 = (torch.rand(n, generator=g) - 0.5) * 0.2
+        w = -(-s // 32)
+        act = torch.zeros((n, w), dtype=torch.int32, device="cuda")
+        pop = torch.zeros(s, dtype=torch.int32, device="cuda")
+        m8 = mask.to(torch.uint8).cuda().contiguous()
+        _lib.check(lib.xpgnn_pack_mask(m8.data_ptr(), s, n, act.data_ptr(), w, pop.data_ptr(), _lib.stream_ptr()))
+        co = CoalitionSet(act, pop, s, n, b)
+        for broadcast in (True, False):
+            batches = [(mask[i:i + b].numpy(), kern[i:i + b], y[i:i + b].reshape(-1, 1) if broadcast else y[i:i + b])
+                       for i in range(0, s, b)]
+            w_ref, losses_ref = train_wlm(batches, w0.numpy(), params)
+            w_dev, losses = fit_surrogate(co, y.cuda(), torch.from_numpy(kern).cuda(), w0.cuda(), params, broadcast)
+            np.testing.assert_allclose(w_dev.cpu().numpy(), w_ref.numpy(), atol=2e-5, rtol=1e-3)
+            np.testing.assert_allclose(losses, losses_ref, rtol=1e-4, atol=1e-9)
+EOF
+echo done
