@@ -264,5 +264,3 @@ def test_wlm_fit_matches_closed_form(lib):
             w_dev, losses = fit_surrogate(co, y.cuda(), torch.from_numpy(kern).cuda(), w0.cuda(), params, broadcast)
             np.testing.assert_allclose(w_dev.cpu().numpy(), w_ref.numpy(), atol=2e-5, rtol=1e-3)
             np.testing.assert_allclose(losses, losses_ref, rtol=1e-4, atol=1e-9)
-EOF
-echo done
