@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""Benchmark of the perturbation hot path (BASELINE.json metric: coalition evals/s + masked GTEPS).
+
+Workload (config.workload = "c3"): BASELINE.json configs[2] -- synthetic homogeneous graph, 1 M nodes /
+20 M edges (uniform), 2 x GCNConv(128) + Linear(128 -> 1), 500 disjoint communities, whole-graph
+computational graph, every conv layer on every row ("full" mode = the work the reference does).
+A step = one pass of the hot path over one batch of synthetic coalitions: each rank evaluates
+`--coalitions-per-gpu` (default 512) coalition rows, so that 8 ranks x 512 = the 4096-coalition job of
+the north star in one step (weak scaling: per-GPU work fixed).
+
+value   : coalition evals/s, masks/graph/weights resident in HBM, CUDA-event timed, max over ranks.
+e2e     : same metric through the public API with HOST coalition masks: pinned (B, N) uint8 rows ->
+          H2D -> bit packing -> masked forward -> D2H of the predictions, all inside the timed region.
+roofline: masked SpMM on coalition-specific activations (layers >= 1), algorithmic bytes per launch
+           / CUDA-event kernel time measured live via xpgnn_profile.
+cpu_baseline / --impl reference: the oracle port of the reference algorithm (block-diagonal
+          materialisation, in1d edge filter, scatter-add GCN) on the host cores, bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (nodes, edges, features, hidden, communities)
+    "c3": (1_000_000, 20_000_000, 128, 128, 500),
+    "c3_tenth": (100_000, 2_000_000, 128, 128, 50),
+    "tiny": (20_000, 400_000, 32, 32, 20),
+}
+
+
+def make_graph(name):
+    n, e, f, h, c = WORKLOADS[name]
+    g = torch.Generator().manual_seed(1234)
+    ei = torch.randint(0, n, (2, e), generator=g)
+    x = torch.randn(n, f, generator=g)
+    com_of = torch.randperm(n, generator=g) % c  # c disjoint, equal communities
+    return n, e, f, h, c, x, ei, com_of
+
+
+def make_model(f, h, seed=7):
+    from torch import nn
+
+    from bikg_graph_explainability_public_b200 import nn as xnn
+
+    torch.manual_seed(seed)
+
+    class GCN2(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv = nn.ModuleList([xnn.GCNConv(f, h), nn.ReLU(), xnn.GCNConv(h, h), nn.ReLU()])
+            self.fc = nn.ModuleList([xnn.Linear(h, 1)])
+
+    return GCN2().eval()
+
+
+def oracle_model(arch, f, h):
+    """Same weights in the oracle's CPU stand-in layers (for the CPU baseline / parity check)."""
+    from oracle import fixture_models as fm
+
+    m = fm.HomoGCN(f, (h, h), (h, 1), final_sigmoid=False)
+    m.load_state_dict(arch.state_dict())
+    return m.eval()
+
+
+def make_masks(n_rows, n, c, com_of, seed):
+    """Coalition rows of the reference's family: row i perturbs community i mod C internally (iid node
+    bits) and switches every other community on/off as a block (antithetic pairs)."""
+    g = torch.Generator().manual_seed(seed)
+    half = (n_rows + 1) // 2
+    ext = torch.rand(half, c, generator=g) < 0.5
+    ext = torch.cat([ext, ~ext])[:n_rows]
+    mask = torch.empty((n_rows, n), dtype=torch.uint8)
+    for i in range(n_rows):
+        row = ext[i][com_of]
+        own = com_of == (i % c)
+        row[own] = torch.rand(int(own.sum()), generator=g) < 0.5
+        mask[i] = row
+    return mask
+
+
+class ClockSampler:
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args, rank):
+    """Reference arm: the oracle port of the reference's CPU algorithm, all host threads."""
+    if rank != 0:
+        return
+    from oracle.xpgnn_oracle import kernel_output
+
+    n, e, f, h, c, x, ei, com_of = make_graph(args.workload)
+    torch.set_num_threads(os.cpu_count())
+    arch = oracle_model(make_model(f, h), f, h)
+    b = args.ref_coalitions
+    mask = make_masks(b * (args.steps + args.warmup), n, c, com_of, 99).bool().numpy()
+    ei_np = ei.numpy()
+    q = 17
+    times = []
+    for i in range(args.steps + args.warmup):
+        t0 = time.perf_counter()
+        kernel_output(mask[i * b:(i + 1) * b], x, ei_np, arch, q)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt)
+    t = float(np.sum(times))
+    value = b * len(times) / t
+    line = {
+        "impl": "reference", "metric": "coalition evals/s", "value": value, "unit": "coalition evals/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(args, n, e, h, c),
+        "masked_gteps": value * 2 * e / 1e9,
+        "cpu_baseline": {"value": value, "unit": "coalition evals/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": "%d coalitions per step of the full %s workload (oracle port of the reference's "
+                                   "block-diagonal path, torch CPU)" % (b, args.workload)},
+        "e2e": {"value": value, "unit": "coalition evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(args, n, e, h, c):
+    return {"workload": args.workload, "nodes": n, "edges": e, "model": "2xGCNConv(%d)+Linear(%d,1)" % (h, h),
+            "communities": c, "coalitions_per_gpu_per_step": args.coalitions_per_gpu, "mode": "full (every conv layer on "
+            "every row of the whole-graph computational graph)", "l2": "inputs larger than L2 (activation tiles of "
+            "16 GiB vs 126 MB L2)", "precision": "fp32"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=list(WORKLOADS))
+    ap.add_argument("--coalitions-per-gpu", type=int, default=512)
+    ap.add_argument("--cpu-coalitions", type=int, default=4, help="coalitions of the CPU baseline sample")
+    ap.add_argument("--ref-coalitions", type=int, default=2, help="coalitions per step of --impl reference")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch.distributed as dist
+
+    from bikg_graph_explainability_public_b200 import _lib
+    from bikg_graph_explainability_public_b200.engine import GraphSpec, MaskedForward
+    from bikg_graph_explainability_public_b200.lowering import lower
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    n, e, f, h, c, x, ei, com_of = make_graph(args.workload)
+    arch = make_model(f, h)
+    q = 17
+    eng = MaskedForward(GraphSpec(x.to(dev), ei.to(dev), [0, n]), lower(arch), [q], prune=False)
+    s_local = args.coalitions_per_gpu
+    w = -(-s_local // 32)
+    mask_host = make_masks(s_local, n, c, com_of, 1000 + rank).pin_memory()
+    mask_dev = torch.empty_like(mask_host, device=dev)
+    act = torch.zeros((n, w), dtype=torch.int32, device=dev)
+    pop = torch.zeros(s_local, dtype=torch.int32, device=dev)
+    y_all = torch.empty((world * s_local, 1), dtype=torch.float32, device=dev)
+
+    def pack():
+        _lib.check(lib.xpgnn_pack_mask(mask_dev.data_ptr(), s_local, n, act.data_ptr(), w, pop.data_ptr(),
+                                       _lib.stream_ptr()))
+
+    def step_resident():
+        y = eng(act, s_local)
+        if world > 1:
+            dist.all_gather_into_tensor(y_all, y)  # the single collective of the path
+            return y_all
+        return y
+
+    def step_e2e():
+        mask_dev.copy_(mask_host, non_blocking=True)
+        pack()
+        return step_resident().cpu()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    mask_dev.copy_(mask_host)
+    pack()
+    for _ in range(max(args.warmup, 3)):
+        y = step_resident()
+    barrier()
+
+    # ---- timed: resident inputs ----
+    lib.xpgnn_profile(1)
+    launches0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            y = step_resident()
+        ev1.record()
+        barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    launches = _lib.launch_count() - launches0
+    prof_ms = (np.zeros(5), np.zeros(5, dtype=np.int64))
+    lib.xpgnn_profile_read(prof_ms[0].ctypes.data, prof_ms[1].ctypes.data)
+    lib.xpgnn_profile(0)
+
+    # ---- timed: end to end from host coalition masks ----
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        y_host = step_e2e()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_total = float(e2e_s.item())
+
+    if rank == 0:
+        evals = world * s_local * args.steps
+        value = evals / (ms_total / 1e3)
+        visits = eng.edge_visits_per_coalition  # kept edges x conv layers
+        # algorithmic bytes of one coalition-layer: col idx + rowptr + bits + read Z once + write
+        e_kept = eng.edges_per_layer[0]
+        b_alg = 4 * e_kept + 4 * (n + 1) + n / 8 + 2 * n * h * 4
+        cats = ["masked_degree", "spmm_invariant_l0", "spmm_tile_l1", "dense", "head"]
+        kern = {k: {"ms": float(prof_ms[0][i]), "launches": int(prof_ms[1][i])} for i, k in enumerate(cats)}
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                peaks = json.load(fh)
+        except OSError:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        dom = "spmm_tile_l1" if kern["spmm_tile_l1"]["ms"] >= kern["spmm_invariant_l0"]["ms"] else "spmm_invariant_l0"
+        tile = eng.tile_coalitions
+        roof = {}
+        for k in ("spmm_tile_l1", "spmm_invariant_l0"):
+            if kern[k]["launches"]:
+                avg_ms = kern[k]["ms"] / kern[k]["launches"]
+                ach = tile * b_alg / (avg_ms / 1e3) / 1e9
+                roof[k] = {"avg_launch_ms": avg_ms, "achieved_gbs": ach, "frac": ach / peak}
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+                traffic = json.load(fh).get(dom)
+        except OSError:
+            pass
+        line = {
+            "metric": "coalition evals/s", "value": value, "unit": "coalition evals/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(args, n, e, h, c),
+            "masked_gteps": value * visits / 1e9,
+            "e2e": {"value": evals / e2e_total, "unit": "coalition evals/s",
+                    "h2d_bytes_per_step": int(mask_host.numel()), "d2h_bytes_per_step": int(y_host.numel() * 4)},
+            "gpu_launches": int(launches),
+            "clocks": clocks.summary(),
+            "roofline": {"bound": "hbm", "kernel": "spmm_masked_kernel (%s)" % dom,
+                         "achieved": roof.get(dom, {}).get("achieved_gbs"), "peak": peak, "unit": "GB/s",
+                         "frac": roof.get(dom, {}).get("frac"), "traffic": traffic,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+                         "algorithmic_bytes_per_launch": tile * b_alg, "coalitions_per_launch": tile,
+                         "per_kernel": roof},
+            "kernels": kern,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args, n, f, h, x, ei, arch, mask_host, q, y_host)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args, n, f, h, x, ei, arch, mask_host, q, y_gpu):
+    """Oracle port on the host cores over a bounded sample of the same workload; also the parity check."""
+    from oracle.xpgnn_oracle import kernel_output
+
+    torch.set_num_threads(os.cpu_count())
+    b = args.cpu_coalitions
+    m = mask_host[:b].bool().numpy()
+    om = oracle_model(arch, f, h)
+    t0 = time.perf_counter()
+    _, y_ref = kernel_output(m, x, ei.numpy(), om, q)
+    dt = time.perf_counter() - t0
+    y_ref = y_ref.numpy().reshape(-1)
+    rel = float(np.max(np.abs(y_gpu.numpy().reshape(-1)[:b] - y_ref) / np.maximum(np.abs(y_ref), 1e-6)))
+    return {"value": b / dt, "unit": "coalition evals/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "%d coalitions of the full %s workload in one batch (%.1f s of CPU work)" % (b, args.workload, dt),
+            "gpu_vs_oracle_max_rel_err": rel}
+
+
+if __name__ == "__main__":
+    main()

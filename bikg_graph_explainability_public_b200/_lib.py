@@ -58,6 +58,8 @@ _SIGNATURES = {
     "xpgnn_forward_workspace_bytes": (i64, [C.POINTER(Plan), i32]),
     "xpgnn_forward": (C.c_int, [C.POINTER(Plan), ptr, i32, i32, i32, ptr, ptr, i64, ptr, ptr]),
     "xpgnn_dense_rows": (C.c_int, [ptr, i64, i32, i32, ptr, ptr, i32, i32, ptr, i32, i32, i32, ptr]),
+    "xpgnn_profile": (C.c_int, [i32]),
+    "xpgnn_profile_read": (C.c_int, [ptr, ptr]),
     "xpgnn_shap_weights": (C.c_int, [ptr, i32, i32, i32, ptr, ptr, i32, ptr, ptr]),
     "xpgnn_wlm_fit": (C.c_int, [ptr, i32, i32, i32, i32, ptr, ptr, ptr, f64, f64, f64, i32, ptr, ptr]),
     "xpgnn_repeat_stats": (C.c_int, [ptr, i32, i32, ptr, ptr, ptr]),

@@ -364,8 +364,37 @@ __global__ void stats_accum_kernel(const unsigned long long* tile_active, int n_
 }
 
 // ------------------------------------------------------------------------------------------ host side
+// Optional per-category kernel timing with CUDA events on the launching stream (bench.py roofline).
+enum { PROF_SCALE = 0, PROF_SPMM_INVARIANT, PROF_SPMM_TILE, PROF_DENSE, PROF_HEAD, PROF_N };
+struct Profile {
+  bool on = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[PROF_N];
+  void reset() {
+    for (auto& v : ev) {
+      for (auto& e : v) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+      v.clear();
+    }
+  }
+};
+static Profile g_prof;
+struct ProfScope {
+  cudaStream_t st;
+  cudaEvent_t stop = nullptr;
+  ProfScope(int cat, cudaStream_t s) : st(s) {
+    if (!g_prof.on) return;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaEventRecord(a, st);
+    g_prof.ev[cat].push_back({a, b});
+    stop = b;
+  }
+  ~ProfScope() { if (stop) cudaEventRecord(stop, st); }
+};
+
 static int launch_dense(const DenseArgs& d, cudaStream_t st) {
   if (d.M <= 0 || d.n_out <= 0) return 0;
+  ProfScope ps(PROF_DENSE, st);
   dim3 grid((unsigned)ceil_div(d.M, DBM), (unsigned)ceil_div(d.n_out, DBN));
   XP_LAUNCH(dense_rows_kernel, grid, 256, 0, st, d);
   return 0;
@@ -373,6 +402,7 @@ static int launch_dense(const DenseArgs& d, cudaStream_t st) {
 
 static int launch_spmm(const SpmmArgs& s, cudaStream_t st) {
   if (s.n_rows <= 0 || s.n_bits <= 0) return 0;
+  ProfScope ps(s.in_s_stride == 0 ? PROF_SPMM_INVARIANT : PROF_SPMM_TILE, st);
   const int grid = (int)std::min<int64_t>(ceil_div(s.n_rows, 8), (int64_t)kNumSMs * 16);
   const bool vec4 = (s.H % 4 == 0) && (s.ld_in % 4 == 0) && (s.ld_out % 4 == 0) && (s.in_s_stride % 4 == 0) &&
                     (s.out_s_stride % 4 == 0) && (((uintptr_t)s.in | (uintptr_t)s.out) % 16 == 0) &&
@@ -469,6 +499,28 @@ using namespace xpgnn;
 
 extern "C" {
 
+int xpgnn_profile(int32_t enable) {
+  g_prof.reset();
+  g_prof.on = enable != 0;
+  return 0;
+}
+
+int xpgnn_profile_read(double* ms_host, int64_t* launches_host) {
+  XP_REQUIRE(ms_host && launches_host, "null argument");
+  for (int c = 0; c < PROF_N; ++c) {
+    double tot = 0.0;
+    for (auto& e : g_prof.ev[c]) {
+      XP_CHECK(cudaEventSynchronize(e.second));
+      float ms = 0.f;
+      XP_CHECK(cudaEventElapsedTime(&ms, e.first, e.second));
+      tot += ms;
+    }
+    ms_host[c] = tot;
+    launches_host[c] = (int64_t)g_prof.ev[c].size();
+  }
+  return 0;
+}
+
 int64_t xpgnn_forward_workspace_bytes(const xpgnn_plan_t* plan, int32_t tile_coalitions) {
   if (!plan || plan->n_layers < 1 || tile_coalitions < 1 || tile_coalitions > 32) return -1;
   std::vector<UniqueCsr> uniq;
@@ -561,6 +613,7 @@ int xpgnn_forward(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32_t
     for (size_t i = 0; i < uniq.size(); ++i) {
       const int rows = uniq[i].hi - uniq[i].lo;
       const int grid = (int)std::min<int64_t>(std::max<int64_t>(ceil_div(rows, 8), 1), (int64_t)kNumSMs * 8);
+      ProfScope ps(PROF_SCALE, st);
       XP_LAUNCH(masked_scale_kernel, grid, 256, 0, st, uniq[i].rowptr, uniq[i].col, act, W, w, uniq[i].lo, uniq[i].hi,
                 uniq[i].kind, lay.scale[i], lay.tile_active);
     }
@@ -626,7 +679,10 @@ int xpgnn_forward(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32_t
       h.y = y + ((int64_t)(w * 32 + b0) - s0) * p->n_query;
       h.tile_active = p->zero_edge_rule ? lay.tile_active : nullptr;
       h.b0 = b0;
-      XP_LAUNCH(head_kernel, nb * p->n_query, 128, sizeof(float) * 2 * max_dim, st, h, max_dim);
+      {
+        ProfScope ps(PROF_HEAD, st);
+        XP_LAUNCH(head_kernel, nb * p->n_query, 128, sizeof(float) * 2 * max_dim, st, h, max_dim);
+      }
       if (stats) {
         long long mult = 0;
         for (int l = 0; l < NL; ++l) mult += p->layers_host[l].n_rel;  // every layer walks every relation once

@@ -188,6 +188,14 @@ int xpgnn_dense_rows(const float* in, int64_t rows, int32_t k, int32_t ld_in, co
                      int32_t n_out, int32_t act, float* out, int32_t ld_out, int32_t accumulate,
                      int32_t precision, void* stream);
 
+/* Measurement hook (bench.py roofline): when enabled, every engine kernel launch is bracketed by
+ * CUDA events on its stream.  xpgnn_profile_read synchronises those events and returns, per
+ * category {masked degree, SpMM on the coalition-invariant operand (layer 0), SpMM on coalition-
+ * specific activations (layers >= 1), dense transform, head}, the summed device time in ms and the
+ * number of launches.  Both arrays are HOST arrays of 5 entries. */
+int xpgnn_profile(int32_t enable);
+int xpgnn_profile_read(double* ms_host, int64_t* launches_host);
+
 /* ------------------------------------------------------------------------------------------
  * a8  SHAP kernel weights
  * replaces: Kernel.compute / original_shap_kernel / approximate_shap_kernel (kernels.py:22-174)
