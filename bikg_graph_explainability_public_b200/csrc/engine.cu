@@ -18,7 +18,10 @@
 #include <algorithm>
 #include <vector>
 
+#include <cstdlib>
+
 #include "common.cuh"
+#include "dense_args.cuh"
 
 namespace xpgnn {
 
@@ -79,12 +82,6 @@ struct SpmmArgs {
   int ld_out;
   int accumulate, act_fn, H;
 };
-
-__device__ __forceinline__ float apply_act(float x, int a) {
-  if (a == XPGNN_ACT_RELU) return fmaxf(x, 0.0f);
-  if (a == XPGNN_ACT_SIGMOID) return 1.0f / (1.0f + expf(-x));
-  return x;
-}
 
 template <int VEC>
 struct Vec;
@@ -217,26 +214,8 @@ __global__ void __launch_bounds__(256) spmm_masked_kernel(const SpmmArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
-// dense row transform (exact fp32 SIMT path): out[m][n] (+)= act(sum_k in[m][k] w[n][k] + b[n])
-// m enumerates (coalition slot s, row): optional row list, per-slot strides.
+// dense row transform, exact fp32 SIMT path (tensor-core path: dense_tc.cu)
 // ------------------------------------------------------------------------------------------
-struct DenseArgs {
-  const float* in;
-  int64_t in_s_stride;
-  int ld_in, k;
-  const float* w;  // [n_out][k]
-  const float* b;
-  int n_out;
-  float* out;
-  int64_t out_s_stride;
-  int ld_out;
-  const int32_t* rows;
-  int rows_per_s, row_lo;  // rows == NULL: row = row_lo + (m % rows_per_s)
-  int64_t M;               // n_slots * rows_per_s
-  int accumulate, act_fn;
-  int dst_lo, dst_hi;      // rows outside [dst_lo, dst_hi) are skipped (row lists of hetero layers)
-};
-
 constexpr int DBM = 64, DBN = 64, DBK = 16;
 
 __global__ void __launch_bounds__(256) dense_rows_kernel(const DenseArgs a) {
@@ -392,9 +371,14 @@ struct ProfScope {
   ~ProfScope() { if (stop) cudaEventRecord(stop, st); }
 };
 
-static int launch_dense(const DenseArgs& d, cudaStream_t st) {
+// precision: DENSE_SIMT exact fp32 FMA | DENSE_TC_TF32X3 fp32 via 3 TF32 MMAs | DENSE_TC_BF16
+static int launch_dense(const DenseArgs& d, cudaStream_t st, int precision = DENSE_SIMT) {
   if (d.M <= 0 || d.n_out <= 0) return 0;
   ProfScope ps(PROF_DENSE, st);
+  if (precision != DENSE_SIMT && d.M >= 1024) {
+    const int mode = precision == DENSE_TC_BF16 ? 1 : 0;
+    if (dense_tc_eligible(d, mode)) return launch_dense_tc(d, mode, st);
+  }
   dim3 grid((unsigned)ceil_div(d.M, DBM), (unsigned)ceil_div(d.n_out, DBN));
   XP_LAUNCH(dense_rows_kernel, grid, 256, 0, st, d);
   return 0;
@@ -532,10 +516,15 @@ int64_t xpgnn_forward_workspace_bytes(const xpgnn_plan_t* plan, int32_t tile_coa
 int xpgnn_dense_rows(const float* in, int64_t rows, int32_t k, int32_t ld_in, const float* w, const float* b, int32_t n_out,
                      int32_t act, float* out, int32_t ld_out, int32_t accumulate, int32_t precision, void* stream) {
   XP_REQUIRE(in && w && out && rows >= 0 && rows < (1ll << 31) && k > 0 && n_out > 0, "bad argument");
-  XP_REQUIRE(precision == 0, "precision 1 (bf16 tcgen05) is not built into this library version");
+  XP_REQUIRE(precision >= 0 && precision <= 2, "precision must be 0 (fp32 SIMT), 1 (bf16 tcgen05) or 2 (tf32x3 tcgen05)");
   DenseArgs d{};
   d.in = in; d.ld_in = ld_in; d.k = k; d.w = w; d.b = b; d.n_out = n_out; d.out = out; d.ld_out = ld_out;
   d.rows_per_s = (int)rows; d.M = rows; d.accumulate = accumulate; d.act_fn = act; d.dst_lo = 0; d.dst_hi = (int)rows;
+  if (precision != DENSE_SIMT) {
+    XP_REQUIRE(dense_tc_eligible(d, precision == DENSE_TC_BF16 ? 1 : 0), "shape not eligible for the tensor-core path");
+    ProfScope ps(PROF_DENSE, (cudaStream_t)stream);
+    return launch_dense_tc(d, precision == DENSE_TC_BF16 ? 1 : 0, (cudaStream_t)stream);
+  }
   return launch_dense(d, (cudaStream_t)stream);
 }
 
@@ -545,7 +534,11 @@ int xpgnn_forward(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32_t
   XP_REQUIRE(p->n_layers >= 1 && p->n_nodes > 0 && p->n_query > 0 && p->query, "empty plan");
   XP_REQUIRE(s0 % 32 == 0 && n_s >= 0 && (int64_t)W * 32 >= (int64_t)s0 + n_s, "coalition range outside the bit matrix");
   XP_REQUIRE(p->n_head <= kMaxHead, "head deeper than 8 layers");
-  XP_REQUIRE(p->precision == 0, "precision 1 (bf16 tcgen05) is not built into this library version");
+  XP_REQUIRE(p->precision == 0 || p->precision == 1, "plan precision must be 0 (fp32) or 1 (bf16 transforms)");
+  // fp32 plans use the 3xTF32 tensor-core transform (error ~2^-20) unless XPGNN_DENSE=simt forces exact FMA
+  const char* dense_env = getenv("XPGNN_DENSE");
+  const int dense_prec = p->precision == 1 ? DENSE_TC_BF16
+                                           : ((dense_env && std::string(dense_env) == "simt") ? DENSE_SIMT : DENSE_TC_TF32X3);
   XP_REQUIRE(!p->prune || p->hop, "prune = 1 needs the hop levels");
   if (n_s == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
@@ -583,14 +576,14 @@ int xpgnn_forward(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32_t
     DenseArgs z{};
     z.in = p->x; z.ld_in = p->f_in; z.k = p->f_in; z.w = R.w_nbr; z.n_out = L0.h_out; z.out = lay.zn[r]; z.ld_out = L0.h_out;
     z.rows_per_s = R.src_hi - R.src_lo; z.row_lo = R.src_lo; z.M = z.rows_per_s; z.dst_lo = 0; z.dst_hi = N;
-    if (launch_dense(z, st)) return 1;
+    if (launch_dense(z, st, dense_prec)) return 1;
     // R0 += b_r (+ X W_root,r^T for SAGE) on the destination range; k = 0 degenerates to "add the bias"
     const bool sage_root = R.conv_kind == XPGNN_CONV_SAGE_MEAN && R.w_root;
     if (sage_root || R.b_nbr) {
       DenseArgs rt = z;
       rt.k = sage_root ? p->f_in : 0; rt.w = sage_root ? R.w_root : R.w_nbr; rt.b = R.b_nbr; rt.out = lay.r0;
       rt.rows_per_s = R.dst_hi - R.dst_lo; rt.row_lo = R.dst_lo; rt.M = rt.rows_per_s; rt.accumulate = 1;
-      if (launch_dense(rt, st)) return 1;
+      if (launch_dense(rt, st, dense_prec)) return 1;
     }
   }
 
@@ -654,12 +647,12 @@ int xpgnn_forward(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32_t
             d.M = (int64_t)nb * d.rows_per_s; d.accumulate = !first[r];
             d.act_fn = (last[r] && !sage_root) ? L.act : XPGNN_ACT_NONE;
             d.dst_lo = R.dst_lo; d.dst_hi = R.dst_hi;  // a pruned row list may hold rows of other node types
-            if (launch_dense(d, st)) return 1;
+            if (launch_dense(d, st, dense_prec)) return 1;
             if (sage_root) {
               DenseArgs rt = d;
               rt.in = cur; rt.in_s_stride = hstride; rt.ld_in = hmax; rt.w = R.w_root; rt.b = nullptr;
               rt.accumulate = 1; rt.act_fn = last[r] ? L.act : XPGNN_ACT_NONE;
-              if (launch_dense(rt, st)) return 1;
+              if (launch_dense(rt, st, dense_prec)) return 1;
             }
           }
         }
