@@ -22,7 +22,7 @@ class MaskPlan(C.Structure):
 
 class Relation(C.Structure):
     _fields_ = [("conv_kind", i32), ("src_lo", i32), ("src_hi", i32), ("dst_lo", i32), ("dst_hi", i32),
-                ("rowptr", ptr), ("col", ptr), ("w_nbr", ptr), ("b_nbr", ptr), ("w_root", ptr)]
+                ("n_edges", i32), ("rowptr", ptr), ("col", ptr), ("w_nbr", ptr), ("b_nbr", ptr), ("w_root", ptr)]
 
 
 class Layer(C.Structure):

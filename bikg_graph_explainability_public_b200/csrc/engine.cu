@@ -30,7 +30,7 @@ namespace xpgnn {
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) masked_scale_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                                                            const uint32_t* __restrict__ act, int W, int w, int row_lo, int row_hi,
-                                                           int kind, float* __restrict__ scale,
+                                                           int kind, float* __restrict__ scale, uint32_t* __restrict__ ebits,
                                                            unsigned long long* __restrict__ tile_active) {
   __shared__ unsigned long long s_active[32];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -44,7 +44,10 @@ __global__ void __launch_bounds__(256) masked_scale_kernel(const int32_t* __rest
     for (int base = e0; base < e1; base += 32) {
       const int e = base + lane;
       uint32_t bits = 0;
-      if (e < e1) bits = act[(int64_t)col[e] * W + w] & av;
+      if (e < e1) {
+        bits = act[(int64_t)col[e] * W + w] & av;
+        ebits[e] = bits;  // bit b: edge e is active in coalition 32 w + b (read by every SpMM of the tile)
+      }
       const int n = min(32, e1 - base);
       for (int j = 0; j < n; ++j) cnt += (__shfl_sync(0xffffffffu, bits, j) >> lane) & 1u;
     }
@@ -65,8 +68,8 @@ __global__ void __launch_bounds__(256) masked_scale_kernel(const int32_t* __rest
 struct SpmmArgs {
   const int32_t* rowptr;
   const int32_t* col;
-  const uint32_t* act;
-  int W, w, b0, n_bits;      // word index, first bit, coalitions in this tile
+  const uint32_t* ebits;     // [E] per-edge activity word of the current 32-coalition word
+  int b0, n_bits;            // first bit, coalitions in this tile
   const float* in;           // gathered operand; in[s * in_s_stride + u * ld_in + c]
   int64_t in_s_stride;       // 0: coalition-invariant operand (layer 0)
   int ld_in;
@@ -133,14 +136,17 @@ __device__ __forceinline__ void gather_edges(const SpmmArgs& a, uint32_t m, int 
 }
 
 template <int VEC>
-__global__ void __launch_bounds__(256) spmm_masked_kernel(const SpmmArgs a) {
+__global__ void __launch_bounds__(256, 4) spmm_masked_kernel(const SpmmArgs a) {
+  // Row-outer, coalition-inner: a row's column indices and edge-activity words are read once and stay
+  // in registers for all coalitions of the tile (<= 64 in-edges; longer rows re-read them from L1).
+  // (The coalition-outer order was measured in round 1: 32x more row visits made it latency bound,
+  //  l1 23.7 -> 29.5 ms, l0 12.2 -> 29.9 ms -- see DESIGN.md.)
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const int chunks = (a.H + 32 * VEC - 1) / (32 * VEC);
   for (int r = blockIdx.x * wpb + wib; r < a.n_rows; r += gridDim.x * wpb) {
     const int v = a.rows ? a.rows[r] : a.row_lo + r;
     if (v < a.dst_lo || v >= a.dst_hi) continue;
     const int e0 = a.rowptr[v], e1 = a.rowptr[v + 1], deg = e1 - e0;
-    const uint32_t av = a.act[(int64_t)v * a.W + a.w];
     const float sc_lane = a.scale[(int64_t)v * 32 + lane];
     int u_reg[2] = {-1, -1};
     uint32_t bits_reg[2] = {0u, 0u};
@@ -149,8 +155,8 @@ __global__ void __launch_bounds__(256) spmm_masked_kernel(const SpmmArgs a) {
       for (int k = 0; k < 2; ++k) {
         const int e = e0 + 32 * k + lane;
         if (e < e1) {
-          u_reg[k] = a.col[e];
-          bits_reg[k] = a.act[(int64_t)u_reg[k] * a.W + a.w] & av;
+          u_reg[k] = __ldg(a.col + e);
+          bits_reg[k] = __ldg(a.ebits + e);
         }
       }
     }
@@ -173,8 +179,8 @@ __global__ void __launch_bounds__(256) spmm_masked_kernel(const SpmmArgs a) {
             int u = -1;
             uint32_t bits = 0;
             if (e < e1) {
-              u = a.col[e];
-              bits = a.act[(int64_t)u * a.W + a.w] & av;
+              u = __ldg(a.col + e);
+              bits = __ldg(a.ebits + e);
             }
             gather_edges<VEC>(a, __ballot_sync(0xffffffffu, (bits >> b) & 1u), u, b, in_s, c0, colok, acc);
           }
@@ -413,6 +419,7 @@ struct Layout {
   std::vector<float*> zn;      // layer-0 per-relation transformed sources (biased pointer: index by global id)
   float* r0 = nullptr;         // layer-0 coalition-invariant addend
   std::vector<float*> scale;   // per unique CSR
+  std::vector<uint32_t*> ebits; // per unique CSR: activity word of every edge for the current coalition word
   unsigned long long* tile_active = nullptr;
   float* hbuf[2] = {nullptr, nullptr};
   float* agg = nullptr;
@@ -424,7 +431,7 @@ struct Layout {
 struct UniqueCsr {
   const int32_t* rowptr;
   const int32_t* col;
-  int kind, lo, hi;
+  int kind, lo, hi, n_edges;
 };
 
 static void collect_unique(const xpgnn_plan_t* p, std::vector<UniqueCsr>& uniq, std::vector<std::vector<int>>& map) {
@@ -438,7 +445,7 @@ static void collect_unique(const xpgnn_plan_t* p, std::vector<UniqueCsr>& uniq, 
       for (size_t i = 0; i < uniq.size(); ++i)
         if (uniq[i].rowptr == R.rowptr && uniq[i].col == R.col && uniq[i].kind == R.conv_kind) id = (int)i;
       if (id < 0) {
-        uniq.push_back({R.rowptr, R.col, R.conv_kind, R.dst_lo, R.dst_hi});
+        uniq.push_back({R.rowptr, R.col, R.conv_kind, R.dst_lo, R.dst_hi, R.n_edges});
         id = (int)uniq.size() - 1;
       }
       map[l][r] = id;
@@ -457,7 +464,10 @@ static Layout carve(const xpgnn_plan_t* p, void* ws, int64_t cap, int tile, cons
     lay.zn.push_back(z ? z - (int64_t)R.src_lo * L0.h_out : nullptr);
   }
   lay.r0 = b.take<float>(N * L0.h_out);
-  for (size_t i = 0; i < uniq.size(); ++i) lay.scale.push_back(b.take<float>(N * 32));
+  for (size_t i = 0; i < uniq.size(); ++i) {
+    lay.scale.push_back(b.take<float>(N * 32));
+    lay.ebits.push_back(b.take<uint32_t>(std::max(uniq[i].n_edges, 1)));
+  }
   lay.tile_active = b.take<unsigned long long>(32);
   int hmax = 0, kmax = 0;
   for (int l = 0; l < p->n_layers; ++l) {
@@ -608,7 +618,7 @@ int xpgnn_forward(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32_t
       const int grid = (int)std::min<int64_t>(std::max<int64_t>(ceil_div(rows, 8), 1), (int64_t)kNumSMs * 8);
       ProfScope ps(PROF_SCALE, st);
       XP_LAUNCH(masked_scale_kernel, grid, 256, 0, st, uniq[i].rowptr, uniq[i].col, act, W, w, uniq[i].lo, uniq[i].hi,
-                uniq[i].kind, lay.scale[i], lay.tile_active);
+                uniq[i].kind, lay.scale[i], lay.ebits[i], lay.tile_active);
     }
     for (int b0 = 0; b0 < bits_in_word; b0 += tile) {
       const int nb = std::min(tile, bits_in_word - b0);
@@ -621,7 +631,7 @@ int xpgnn_forward(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32_t
         for (int r = 0; r < L.n_rel; ++r) {
           const xpgnn_relation_t& R = L.rel_host[r];
           SpmmArgs s{};
-          s.rowptr = R.rowptr; s.col = R.col; s.act = act; s.W = W; s.w = w; s.b0 = b0; s.n_bits = nb;
+          s.rowptr = R.rowptr; s.col = R.col; s.ebits = lay.ebits[umap[l][r]]; s.b0 = b0; s.n_bits = nb;
           s.scale = lay.scale[umap[l][r]]; s.kind = R.conv_kind;
           s.rows = p->prune ? lay.rows[l] : nullptr;
           s.n_rows = p->prune ? n_rows[l] : (R.dst_hi - R.dst_lo);

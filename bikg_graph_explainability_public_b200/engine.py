@@ -91,7 +91,7 @@ class MaskedForward:
                     sel = graph.edge_type.to(dev) == graph.edge_type_names.index(key)
                     src, dst = ei[0][sel], ei[1][sel]
                 rowptr, col = build_csr(src, dst, n, drop_self_loops=(kind == "gcn"))
-                csr_cache[ck] = (rowptr, col, int(src.numel()))
+                csr_cache[ck] = (rowptr, col, int(rowptr[-1].item()))
             return csr_cache[ck]
 
         f_in = int(x.shape[1])
@@ -114,6 +114,7 @@ class MaskedForward:
                 R.conv_kind = _KIND[r.kind]
                 R.src_lo, R.src_hi = rng(src_t)
                 R.dst_lo, R.dst_hi = rng(dst_t)
+                R.n_edges = e_r
                 R.rowptr, R.col = rowptr.data_ptr(), col.data_ptr()
                 R.w_nbr = w_nbr.data_ptr()
                 R.b_nbr = _lib.dptr(b)
@@ -160,6 +161,10 @@ class MaskedForward:
             raise _lib.XpgnnError("graph does not fit: %d bytes of workspace needed, %d available" % (need, budget))
         self.tile_coalitions = tile
         self.workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+
+    @staticmethod
+    def _kept_edges(rowptr):
+        return int(rowptr[-1].item())
 
     @staticmethod
     def _weight(w, k, dev):

@@ -134,6 +134,7 @@ typedef struct {
   int32_t conv_kind;
   int32_t src_lo, src_hi;     /* flattened id range of the source node type                 */
   int32_t dst_lo, dst_hi;     /* flattened id range of the destination node type            */
+  int32_t n_edges;            /* entries of col (after self-loop removal for GCN)            */
   const int32_t* rowptr;      /* [N+1] in-edges by flattened destination id                  */
   const int32_t* col;         /* [E_r] flattened source ids (GCN: self loops already dropped) */
   const float* w_nbr;         /* [h_out][h_in]  GCN lin.weight | SAGE lin_l.weight            */

@@ -34,7 +34,7 @@ def test_struct_layouts_match_header():
     from bikg_graph_explainability_public_b200 import _lib
 
     assert C.sizeof(_lib.MaskPlan) == 4 * 4 + 9 * 8
-    assert C.sizeof(_lib.Relation) == 5 * 4 + 4 + 5 * 8
+    assert C.sizeof(_lib.Relation) == 6 * 4 + 5 * 8
     assert C.sizeof(_lib.Layer) == 4 + 4 + 8 + 3 * 4 + 4
     assert C.sizeof(_lib.Dense) == 3 * 4 + 4 + 2 * 8
     assert _lib.Plan.x.offset == 8 and _lib.Plan.layers_host.offset == 24 and _lib.Plan.query.offset == 56
