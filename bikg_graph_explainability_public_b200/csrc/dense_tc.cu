@@ -123,7 +123,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const DenseArgs
   __shared__ uint64_t bar_stage[Cfg::STAGES];
   __shared__ uint64_t bar_acc;
   __shared__ uint32_t tmem_base_sh;
-  __shared__ int64_t in_off[TM], out_off[TM];
+  __shared__ int64_t out_off[TM];
+  __shared__ __align__(16) float s_bias[256];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int K = a.k;                                  // multiple of Cfg::KC
@@ -133,6 +134,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const DenseArgs
   uint8_t* sA = smem + (size_t)b_part_bytes * Cfg::PARTS;  // [STAGES][PARTS][TM x KC]
 
   if (warp == 0) tmem_alloc(&tmem_base_sh, tmem_cols);
+  s_bias[tid] = (a.b && tid < a.n_out) ? a.b[tid] : 0.0f;  // TC_THREADS == 256 >= n_pad
   if (tid == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) mbar_init(&bar_stage[s], 1);
     mbar_init(&bar_acc, 1);
@@ -177,92 +179,128 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const DenseArgs
   const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
   const int n_chunks = K / Cfg::KC;
   const int64_t n_tiles = (a.M + TM - 1) / TM;
-  uint32_t uses[Cfg::STAGES] = {0u, 0u};
+  uint32_t uses0 = 0u, uses1 = 0u;  // per-stage use counters (scalars: a dynamically indexed array would live in local memory)
   uint32_t chunk_ctr = 0, tile_ctr = 0;
 
   // loader mapping: per warp instruction 8 rows x 4 sixteen-byte columns; 32 units of (row group, half)
   const int lr = lane & 7, lj = lane >> 3;
+  constexpr int NV = MODE == 0 ? 4 : 8;  // float4 registers per thread per K chunk
 
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_ctr) {
-    if (tid < TM) {
-      const int64_t m = tile * TM + tid;
-      int64_t io = -1, oo = -1;
-      if (m < a.M) {
-        const int64_t s = m / a.rows_per_s;
-        const int rr = (int)(m - s * a.rows_per_s);
-        const int64_t v = a.rows ? a.rows[rr] : a.row_lo + rr;
-        if (v >= a.dst_lo && v < a.dst_hi) {
-          io = s * a.in_s_stride + v * a.ld_in;
-          oo = s * a.out_s_stride + v * a.ld_out;
-        }
+  // global -> registers for one (tile, K chunk); rows beyond M / outside the destination range read as 0
+  auto load_item = [&](int64_t tile, int kc, float4 (&buf)[NV]) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int unit = warp * 4 + it;
+      const int r = (unit >> 1) * 8 + lr;
+      const int j = (unit & 1) * 4 + lj;
+      const uint32_t m = (uint32_t)tile * TM + r;  // M < 2^31 (checked on the host): 32-bit div, not 64-bit
+      int64_t io = -1;
+      if (m < (uint32_t)a.M) {
+        const uint32_t sl = m / (uint32_t)a.rows_per_s;
+        const int rr = (int)(m - sl * (uint32_t)a.rows_per_s);
+        const int v = a.rows ? a.rows[rr] : a.row_lo + rr;
+        if (v >= a.dst_lo && v < a.dst_hi) io = (int64_t)sl * a.in_s_stride + (int64_t)v * a.ld_in;
       }
-      in_off[tid] = io;
+      if (MODE == 0) {
+        buf[it] = io >= 0 ? __ldg(reinterpret_cast<const float4*>(a.in + io + kc * Cfg::KC + j * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        buf[2 * it] = io >= 0 ? __ldg(reinterpret_cast<const float4*>(a.in + io + kc * Cfg::KC + j * 8)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        buf[2 * it + 1] = io >= 0 ? __ldg(reinterpret_cast<const float4*>(a.in + io + kc * Cfg::KC + j * 8 + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  };
+  // item i (flattened over this CTA's tiles and K chunks) -> (tile, kc); tile < 0 when past the end
+  auto item_tile = [&](int64_t i) -> int64_t {
+    const int64_t t = (int64_t)blockIdx.x + (i / n_chunks) * gridDim.x;
+    return t < n_tiles ? t : -1;
+  };
+
+  // Two chunks are always in flight ahead of the one being staged (1 CTA/SM: latency hiding is explicit).
+  // The three register buffers rotate by unrolling, not by moves -- a move would wait for the load.
+  float4 b0[NV], b1[NV], b2[NV];
+  int64_t item = 0, tile = blockIdx.x;
+  int kc = 0;
+  if (item_tile(0) >= 0) load_item(item_tile(0), 0, b0);
+  if (item_tile(1) >= 0) load_item(item_tile(1), 1 % n_chunks, b1);
+
+  auto step = [&](float4 (&use)[NV], float4 (&pre)[NV]) -> bool {
+    if (tile >= n_tiles) return false;
+    if (kc == 0 && tid < TM) {
+      const uint32_t m = (uint32_t)tile * TM + tid;
+      int64_t oo = -1;
+      if (m < (uint32_t)a.M) {
+        const uint32_t s = m / (uint32_t)a.rows_per_s;
+        const int rr = (int)(m - s * (uint32_t)a.rows_per_s);
+        const int v = a.rows ? a.rows[rr] : a.row_lo + rr;
+        if (v >= a.dst_lo && v < a.dst_hi) oo = (int64_t)s * a.out_s_stride + (int64_t)v * a.ld_out;
+      }
       out_off[tid] = oo;
     }
+    {
+      const int64_t t2 = item_tile(item + 2);
+      if (t2 >= 0) load_item(t2, (int)((item + 2) % n_chunks), pre);
+    }
+    const int st = chunk_ctr & 1;
+    const uint32_t used = st ? uses1 : uses0;
+    if (used > 0) mbar_wait(&bar_stage[st], (used - 1) & 1);  // MMAs that read this stage are done
+    uint8_t* stage = sA + (size_t)st * Cfg::A_STAGE_BYTES;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int unit = warp * 4 + it;
+      const int r = (unit >> 1) * 8 + lr;
+      const int j = (unit & 1) * 4 + lj;
+      const uint32_t off = core_off(r, j, 8);
+      if (MODE == 0) {
+        const float4 v = use[it];
+        float4 hi, lo;
+        hi.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); lo.x = v.x - hi.x;
+        hi.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); lo.y = v.y - hi.y;
+        hi.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); lo.z = v.z - hi.z;
+        hi.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); lo.w = v.w - hi.w;
+        *reinterpret_cast<float4*>(stage + off) = hi;
+        *reinterpret_cast<float4*>(stage + TM * KC_BYTES + off) = lo;
+      } else {
+        const float4 v0 = use[(2 * it) % NV], v1 = use[(2 * it + 1) % NV];
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(v0.x, v0.y), p1 = __floats2bfloat162_rn(v0.z, v0.w);
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(v1.x, v1.y), p3 = __floats2bfloat162_rn(v1.z, v1.w);
+        uint4 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+        pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
+        *reinterpret_cast<uint4*>(stage + off) = pk;
+      }
+    }
+    fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
+    tc_fence_before();
     __syncthreads();
-    for (int kc = 0; kc < n_chunks; ++kc, ++chunk_ctr) {
-      const int st = chunk_ctr % Cfg::STAGES;
-      if (uses[st] > 0) mbar_wait(&bar_stage[st], (uses[st] - 1) & 1);  // MMAs that read this stage are done
-      uint8_t* stage = sA + (size_t)st * Cfg::A_STAGE_BYTES;
-      // 128 rows x 8 sixteen-byte columns = 32 units of (8 rows x 4 columns); 8 warps x 4 units
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t a_hi = sA_addr + st * Cfg::A_STAGE_BYTES;
+      const uint32_t a_lo = a_hi + TM * KC_BYTES;
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const int unit = warp * 4 + it;
-        const int r = (unit >> 1) * 8 + lr;
-        const int j = (unit & 1) * 4 + lj;
-        const int64_t io = in_off[r];
-        const uint32_t off = core_off(r, j, 8);
+      for (int ks = 0; ks < Cfg::KC / Cfg::UK; ++ks) {
+        // one MMA consumes 2 sixteen-byte columns (32 bytes of K)
+        const uint32_t a_off = ks * 2 * 128;
+        const uint32_t b_off = (kc * (KC_BYTES / 16) + ks * 2) * 128;
+        const uint64_t da_hi = smem_desc(a_hi + a_off, 128, 8 * 128);
+        const uint64_t db_hi = smem_desc(sB_addr + b_off, 128, kb16 * 128);
+        const uint32_t first = (kc == 0 && ks == 0) ? 0u : 1u;
+        umma<MODE>(tmem_base, da_hi, db_hi, idesc, first);
         if (MODE == 0) {
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (io >= 0) v = __ldg(reinterpret_cast<const float4*>(a.in + io + kc * Cfg::KC + j * 4));
-          float4 hi, lo;
-          hi.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); lo.x = v.x - hi.x;
-          hi.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); lo.y = v.y - hi.y;
-          hi.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); lo.z = v.z - hi.z;
-          hi.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); lo.w = v.w - hi.w;
-          *reinterpret_cast<float4*>(stage + off) = hi;
-          *reinterpret_cast<float4*>(stage + TM * KC_BYTES + off) = lo;
-        } else {
-          float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-          if (io >= 0) {
-            v0 = __ldg(reinterpret_cast<const float4*>(a.in + io + kc * Cfg::KC + j * 8));
-            v1 = __ldg(reinterpret_cast<const float4*>(a.in + io + kc * Cfg::KC + j * 8 + 4));
-          }
-          __nv_bfloat162 p0 = __floats2bfloat162_rn(v0.x, v0.y), p1 = __floats2bfloat162_rn(v0.z, v0.w);
-          __nv_bfloat162 p2 = __floats2bfloat162_rn(v1.x, v1.y), p3 = __floats2bfloat162_rn(v1.z, v1.w);
-          uint4 pk;
-          pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
-          pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
-          *reinterpret_cast<uint4*>(stage + off) = pk;
+          const uint64_t da_lo = smem_desc(a_lo + a_off, 128, 8 * 128);
+          const uint64_t db_lo = smem_desc(sB_addr + b_part_bytes + b_off, 128, kb16 * 128);
+          umma<MODE>(tmem_base, da_lo, db_hi, idesc, 1u);
+          umma<MODE>(tmem_base, da_hi, db_lo, idesc, 1u);
         }
       }
-      fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
-      tc_fence_before();
-      __syncthreads();
-      if (tid == 0) {
-        tc_fence_after();
-        const uint32_t a_hi = sA_addr + st * Cfg::A_STAGE_BYTES;
-        const uint32_t a_lo = a_hi + TM * KC_BYTES;
-#pragma unroll
-        for (int ks = 0; ks < Cfg::KC / Cfg::UK; ++ks) {
-          // one MMA consumes 2 sixteen-byte columns (32 bytes of K)
-          const uint32_t a_off = ks * 2 * 128;
-          const uint32_t b_off = (kc * (KC_BYTES / 16) + ks * 2) * 128;
-          const uint64_t da_hi = smem_desc(a_hi + a_off, 128, 8 * 128);
-          const uint64_t db_hi = smem_desc(sB_addr + b_off, 128, kb16 * 128);
-          const uint32_t first = (kc == 0 && ks == 0) ? 0u : 1u;
-          umma<MODE>(tmem_base, da_hi, db_hi, idesc, first);
-          if (MODE == 0) {
-            const uint64_t da_lo = smem_desc(a_lo + a_off, 128, 8 * 128);
-            const uint64_t db_lo = smem_desc(sB_addr + b_part_bytes + b_off, 128, kb16 * 128);
-            umma<MODE>(tmem_base, da_lo, db_hi, idesc, 1u);
-            umma<MODE>(tmem_base, da_hi, db_lo, idesc, 1u);
-          }
-        }
-        umma_commit(&bar_stage[st]);
-        if (kc == n_chunks - 1) umma_commit(&bar_acc);
-      }
-      uses[st]++;
+      umma_commit(&bar_stage[st]);
+      if (kc == n_chunks - 1) umma_commit(&bar_acc);
+    }
+    if (st) ++uses1; else ++uses0;
+    ++chunk_ctr;
+    ++item;
+    if (kc != n_chunks - 1) {
+      ++kc;
+      return true;
     }
     // ---- epilogue: TMEM -> registers -> bias / accumulate / activation -> global ----
     mbar_wait(&bar_acc, tile_ctr & 1);
@@ -270,41 +308,60 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const DenseArgs
     {
       const int row = (warp & 3) * 32 + lane;          // TMEM lane == tile row; warp w may touch lanes 32*(w%4)..
       const int64_t oo = out_off[row];
+      // ReLU and identity share one branch-free path (max with 0 or -inf); sigmoid is a separate loop
+      const float lower = a.act_fn == XPGNN_ACT_RELU ? 0.0f : -INFINITY;
+      const bool vec_ok = (a.n_out & 3) == 0 && (a.ld_out & 3) == 0 && (a.out_s_stride & 3) == 0;
       for (int c0 = (warp >> 2) * 32; c0 < n_pad; c0 += 64) {
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, r);
-        if (oo >= 0) {
+        if (oo < 0) continue;
+        if (vec_ok) {
+          float4 prev[8];
+          if (a.accumulate) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              prev[c] = (c0 + 4 * c < a.n_out) ? *reinterpret_cast<const float4*>(a.out + oo + c0 + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
 #pragma unroll
           for (int c = 0; c < 32; c += 4) {
             const int n = c0 + c;
-            if (n + 3 < a.n_out && ((oo + n) & 3) == 0) {
-              float4 v = make_float4(__uint_as_float(r[c]), __uint_as_float(r[c + 1]), __uint_as_float(r[c + 2]), __uint_as_float(r[c + 3]));
-              if (a.b) {
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(a.b + n));
-                v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
-              }
-              float4* op = reinterpret_cast<float4*>(a.out + oo + n);
-              if (a.accumulate) {
-                const float4 p = *op;
-                v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
-              }
-              v.x = apply_act(v.x, a.act_fn); v.y = apply_act(v.y, a.act_fn);
-              v.z = apply_act(v.z, a.act_fn); v.w = apply_act(v.w, a.act_fn);
-              *op = v;
-            } else {
-              for (int i = 0; i < 4; ++i) {
-                if (n + i >= a.n_out) break;
-                float x = __uint_as_float(r[c + i]) + (a.b ? __ldg(a.b + n + i) : 0.0f);
-                if (a.accumulate) x += a.out[oo + n + i];
-                a.out[oo + n + i] = apply_act(x, a.act_fn);
-              }
+            if (n >= a.n_out) break;
+            const float4 bb = *reinterpret_cast<const float4*>(s_bias + n);
+            float4 v = make_float4(__uint_as_float(r[c]) + bb.x, __uint_as_float(r[c + 1]) + bb.y, __uint_as_float(r[c + 2]) + bb.z,
+                                   __uint_as_float(r[c + 3]) + bb.w);
+            if (a.accumulate) {
+              v.x += prev[c >> 2].x; v.y += prev[c >> 2].y; v.z += prev[c >> 2].z; v.w += prev[c >> 2].w;
             }
+            if (a.act_fn == XPGNN_ACT_SIGMOID) {
+              v.x = apply_act(v.x, XPGNN_ACT_SIGMOID); v.y = apply_act(v.y, XPGNN_ACT_SIGMOID);
+              v.z = apply_act(v.z, XPGNN_ACT_SIGMOID); v.w = apply_act(v.w, XPGNN_ACT_SIGMOID);
+            } else {
+              v.x = fmaxf(v.x, lower); v.y = fmaxf(v.y, lower); v.z = fmaxf(v.z, lower); v.w = fmaxf(v.w, lower);
+            }
+            *reinterpret_cast<float4*>(a.out + oo + n) = v;
+          }
+        } else {
+          for (int c = 0; c < 32; ++c) {
+            const int n = c0 + c;
+            if (n >= a.n_out) break;
+            float x = __uint_as_float(r[c]) + s_bias[n];
+            if (a.accumulate) x += a.out[oo + n];
+            a.out[oo + n] = apply_act(x, a.act_fn);
           }
         }
       }
     }
     tc_fence_before();
     __syncthreads();  // accumulator tile and the row offsets may be reused
+    kc = 0;
+    tile += gridDim.x;
+    ++tile_ctr;
+    return true;
+  };
+  while (true) {
+    if (!step(b0, b2)) break;
+    if (!step(b1, b0)) break;
+    if (!step(b2, b1)) break;
   }
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
@@ -314,6 +371,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const DenseArgs
 static bool tc_eligible(const DenseArgs& d, int mode) {
   const int kc = mode == 0 ? 32 : 64;
   if (d.k <= 0 || d.k % kc != 0 || d.n_out < 8 || d.n_out > 256) return false;
+  if (d.M >= (1ll << 31) - 256 || d.rows_per_s <= 0) return false;
   if (d.ld_in % 4 != 0 || d.in_s_stride % 4 != 0 || ((uintptr_t)d.in & 15) != 0 || ((uintptr_t)d.w & 15) != 0) return false;
   const int n_pad = (d.n_out + 15) / 16 * 16;
   const size_t smem = (size_t)n_pad * d.k * (mode == 0 ? 8 : 2) + (size_t)TcCfg<0>::STAGES * TM * KC_BYTES * (mode == 0 ? 2 : 1);
