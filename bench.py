@@ -163,7 +163,7 @@ def run_reference(args, rank):
                                    "block-diagonal path, torch CPU)" % (b, args.workload)},
         "e2e": {"value": value, "unit": "coalition evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def config_dict(args, n, e, h, c):
@@ -173,7 +173,25 @@ def config_dict(args, n, e, h, c):
             "16 GiB vs 126 MB L2)", "precision": "fp32"}
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """Libraries (NCCL's version banner) write to fd 1; the contract is ONE JSON line on stdout.  Point fd 1 at
+    stderr for the whole run and keep the real stdout for the final line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -325,7 +343,7 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, n, f, h, x, ei, arch, mask_host, q, y_host)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

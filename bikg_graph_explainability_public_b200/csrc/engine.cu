@@ -22,6 +22,7 @@
 
 #include "common.cuh"
 #include "dense_args.cuh"
+#include "fused.cuh"
 
 namespace xpgnn {
 
@@ -423,6 +424,7 @@ struct Layout {
   unsigned long long* tile_active = nullptr;
   float* hbuf[2] = {nullptr, nullptr};
   float* agg = nullptr;
+  std::vector<std::vector<float*>> wimg;  // per layer >= 1, per relation: TF32 hi/lo image of W for the fused kernel
   std::vector<int32_t*> rows;  // per layer (prune)
   int32_t* row_counts = nullptr;
   int64_t bytes = 0;
@@ -479,6 +481,10 @@ static Layout carve(const xpgnn_plan_t* p, void* ws, int64_t cap, int tile, cons
     lay.hbuf[1] = b.take<float>((int64_t)tile * N * hmax);
     lay.agg = b.take<float>((int64_t)tile * N * kmax);
   }
+  lay.wimg.resize(p->n_layers);
+  for (int l = 1; l < p->n_layers; ++l)
+    for (int r = 0; r < p->layers_host[l].n_rel; ++r)
+      lay.wimg[l].push_back(b.take<float>(fused_w_image_bytes((p->layers_host[l].h_in + 31) / 32 * 32, p->layers_host[l].h_out) / 4));
   if (p->prune) {
     for (int l = 0; l < p->n_layers; ++l) lay.rows.push_back(b.take<int32_t>(N));
     lay.row_counts = b.take<int32_t>(p->n_layers);
@@ -609,6 +615,28 @@ int xpgnn_forward(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32_t
         }
   };
 
+  // ---- fused SpMM + tcgen05 transform for layers >= 1 (single relation per destination range, no row list) ----
+  const char* fused_env = getenv("XPGNN_FUSED");
+  const bool fused_on = dense_prec == DENSE_TC_TF32X3 && !p->prune && !(fused_env && std::string(fused_env) == "0");
+  const char* sb_env = getenv("XPGNN_FUSED_SB");
+  const int fused_sb = sb_env ? atoi(sb_env) : 0;
+  std::vector<std::vector<char>> use_fused(NL);
+  for (int l = 1; l < NL; ++l) {
+    const xpgnn_layer_t& L = p->layers_host[l];
+    std::vector<char> first, last;
+    first_last(L, first, last);
+    use_fused[l].assign(L.n_rel, 0);
+    for (int r = 0; r < L.n_rel; ++r) {
+      const xpgnn_relation_t& R = L.rel_host[r];
+      const bool sage_root = R.conv_kind == XPGNN_CONV_SAGE_MEAN && R.w_root;
+      if (fused_on && first[r] && last[r] && !sage_root &&
+          fused_eligible(L.h_in, L.h_out, hmax, hmax, hstride, hstride, lay.hbuf[0], lay.hbuf[1])) {
+        use_fused[l][r] = 1;
+        if (fused_build_w_image(R.w_nbr, L.h_out, L.h_in, lay.wimg[l][r], st)) return 1;
+      }
+    }
+  }
+
   const int w_first = s0 / 32, w_last = (s0 + n_s - 1) / 32;
   for (int w = w_first; w <= w_last; ++w) {
     const int bits_in_word = std::min(32, s0 + n_s - w * 32);
@@ -642,6 +670,15 @@ int xpgnn_forward(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32_t
             s.out = cur; s.out_s_stride = hstride; s.ld_out = hmax;
             s.accumulate = !first[r]; s.act_fn = last[r] ? L.act : XPGNN_ACT_NONE;
             if (launch_spmm(s, st)) return 1;
+          } else if (use_fused[l][r]) {  // aggregate + transform in one kernel, the aggregate never leaves the SM
+            FusedArgs f{};
+            f.rowptr = R.rowptr; f.col = R.col; f.ebits = lay.ebits[umap[l][r]]; f.scale = lay.scale[umap[l][r]];
+            f.kind = R.conv_kind; f.in = cur; f.in_s_stride = hstride; f.ld_in = hmax; f.K = L.h_in;
+            f.w_image = lay.wimg[l][r]; f.b = R.b_nbr; f.n_out = L.h_out; f.out = nxt; f.out_s_stride = hstride;
+            f.ld_out = hmax; f.act_fn = L.act; f.row_lo = R.dst_lo; f.n_rows = R.dst_hi - R.dst_lo;
+            f.b0 = b0; f.n_bits = nb; f.SB = fused_sb; f.slot_major = fused_sb > 0 && fused_sb < 32;
+            ProfScope ps(PROF_SPMM_TILE, st);
+            if (launch_fused(f, st)) return 1;
           } else {       // aggregate-first: masked SpMM on the activations, then the dense transform
             s.in = cur; s.in_s_stride = hstride; s.ld_in = hmax; s.H = L.h_in;
             s.addend = nullptr; s.ld_add = 0;

@@ -237,6 +237,35 @@ def test_engine_matches_oracle_on_random_coalitions(kind, seed, lib):
     np.testing.assert_allclose(eng8(act, s)[:, 0].cpu().numpy(), y, rtol=1e-6, atol=1e-7)
 
 
+@pytest.mark.parametrize("hidden", [(32, 32), (64, 128, 64), (128, 128)])
+def test_fused_spmm_dense_matches_oracle(hidden, lib, monkeypatch):
+    """Layers >= 1 through the fused SpMM + tcgen05 (TF32x3) kernel, vs the oracle and vs the unfused path."""
+    from bikg_graph_explainability_public_b200 import _lib
+    from bikg_graph_explainability_public_b200.engine import GraphSpec, MaskedForward
+    from bikg_graph_explainability_public_b200.lowering import lower
+    from oracle.xpgnn_oracle import kernel_output
+
+    x, ei, arch, mask, q = _random_model_case(3, "gcn", n=700, e=6000, f=40, hidden=hidden, s=75)
+    s, n = mask.shape
+    _, y_ref = kernel_output(mask.numpy(), x, ei.numpy(), arch, q)
+    m8 = mask.to(torch.uint8).cuda().contiguous()
+    w = -(-s // 32)
+    act = torch.zeros((n, w), dtype=torch.int32, device="cuda")
+    _lib.check(lib.xpgnn_pack_mask(m8.data_ptr(), s, n, act.data_ptr(), w, None, _lib.stream_ptr()))
+    ys = {}
+    for fused in ("1", "0"):
+        monkeypatch.setenv("XPGNN_FUSED", fused)
+        eng = MaskedForward(GraphSpec(x.cuda(), ei.cuda(), [0, n]), lower(arch), [q])
+        ys[fused] = eng(act, s)[:, 0].cpu().numpy()
+        np.testing.assert_allclose(ys[fused], y_ref.numpy().reshape(-1), rtol=Y_RTOL, atol=Y_ATOL)
+    np.testing.assert_allclose(ys["1"], ys["0"], rtol=2e-5, atol=1e-6)
+    # coalition-major tiles (128 rows x 1 slot) and a memory-limited 8-coalition tile give the same numbers
+    monkeypatch.setenv("XPGNN_FUSED", "1")
+    monkeypatch.setenv("XPGNN_FUSED_SB", "1")
+    eng = MaskedForward(GraphSpec(x.cuda(), ei.cuda(), [0, n]), lower(arch), [q], tile_coalitions=8)
+    np.testing.assert_allclose(eng(act, s)[:, 0].cpu().numpy(), ys["1"], rtol=2e-5, atol=1e-6)
+
+
 def test_wlm_fit_matches_closed_form(lib):
     """Fit kernels vs the oracle's torch-autograd port on random data, both target layouts."""
     from bikg_graph_explainability_public_b200 import _lib
