@@ -170,7 +170,9 @@ def config_dict(args, n, e, h, c):
     return {"workload": args.workload, "nodes": n, "edges": e, "model": "2xGCNConv(%d)+Linear(%d,1)" % (h, h),
             "communities": c, "coalitions_per_gpu_per_step": args.coalitions_per_gpu, "mode": "full (every conv layer on "
             "every row of the whole-graph computational graph)", "l2": "inputs larger than L2 (activation tiles of "
-            "16 GiB vs 126 MB L2)", "precision": "fp32"}
+            "16 GiB vs 126 MB L2)", "precision": getattr(args, "precision", "fp32") + (
+                " (fp32 storage, dense transforms as 3xTF32 tcgen05 MMAs)" if getattr(args, "precision", "fp32") == "fp32"
+                else " transforms (fp32 storage, bf16 tcgen05 MMAs, fp32 accumulate)")}
 
 
 _REAL_STDOUT = None
@@ -202,6 +204,8 @@ def main():
     ap.add_argument("--cpu-coalitions", type=int, default=4, help="coalitions of the CPU baseline sample")
     ap.add_argument("--ref-coalitions", type=int, default=2, help="coalitions per step of --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"],
+                    help="fp32: TF32x3 tensor-core transforms (1e-4 parity bar); bf16: bf16 transforms (2e-2 bar)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -225,7 +229,7 @@ def main():
     n, e, f, h, c, x, ei, com_of = make_graph(args.workload)
     arch = make_model(f, h)
     q = 17
-    eng = MaskedForward(GraphSpec(x.to(dev), ei.to(dev), [0, n]), lower(arch), [q], prune=False)
+    eng = MaskedForward(GraphSpec(x.to(dev), ei.to(dev), [0, n]), lower(arch), [q], prune=False, precision=args.precision)
     s_local = args.coalitions_per_gpu
     w = -(-s_local // 32)
     mask_host = make_masks(s_local, n, c, com_of, 1000 + rank).pin_memory()
@@ -326,7 +330,8 @@ def main():
         line = {
             "metric": "coalition evals/s", "value": value, "unit": "coalition evals/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
             "config": config_dict(args, n, e, h, c),
             "masked_gteps": value * visits / 1e9,
             "e2e": {"value": evals / e2e_total, "unit": "coalition evals/s",

@@ -173,100 +173,106 @@ __global__ void __launch_bounds__(F_THREADS, 1) spmm_dense_fused_kernel(const Fu
     const int rb = a.slot_major ? (int)(t % n_rb) : (int)(t / n_sb);
     const int sb = a.slot_major ? (int)(t / n_rb) : (int)(t % n_sb);
     // ------------------------------------------------ gather phase: 16 warps x 8 (row, slot) pairs
-    int v_prev = -1, e0 = 0, e1 = 0, my_u = -1;
-    uint32_t my_bits = 0;
-#pragma unroll 1
-    for (int i = 0; i < 8; ++i) {
-      const int p = warp * 8 + i;                       // A row of the tile
-      const int rl = p / SB, sl = p - rl * SB;
-      const int r = rb * RB + rl, s = sb * SB + sl;     // node row index in the range, slot in the tile
-      const bool valid = r < a.n_rows && s < a.n_bits;
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      float dv = 0.f;
-      int v = -1;
-      if (valid) {
-        v = a.row_lo + r;
-        const int b = a.b0 + s;
-        const float* in_s = a.in + (int64_t)s * a.in_s_stride;
-        if (v != v_prev) {
-          v_prev = v;
-          e0 = a.rowptr[v];
-          e1 = a.rowptr[v + 1];
-          const int e = e0 + lane;
-          my_u = -1;
-          my_bits = 0;
-          if (e < e1) {
-            my_u = __ldg(a.col + e);
-            my_bits = __ldg(a.ebits + e);
-          }
+    // SB >= 8 (host guarantees it): the 8 pairs of a warp share ONE node row and differ in the coalition slot,
+    // so the row's column indices / activity words are loaded once and the 8 slots advance in lockstep with
+    // 8 independent 512-byte gathers in flight per warp (1 CTA/SM: memory-level parallelism must be explicit).
+    {
+      const int p0 = warp * 8;
+      const int rl = p0 / SB, sl0 = p0 - rl * SB;
+      const int r = rb * RB + rl;
+      const bool row_ok = r < a.n_rows;
+      const int v = a.row_lo + r;
+      float4 acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      int e0 = 0, e1 = 0;
+      if (row_ok) {
+        e0 = a.rowptr[v];
+        e1 = a.rowptr[v + 1];
+      }
+      const int s_base = sb * SB + sl0;                 // first slot of this warp inside the tile
+      const int bbase = a.b0 + s_base;
+      for (int base = e0; base < e1; base += 32) {
+        const int e = base + lane;
+        int u_l = -1;
+        uint32_t bits_l = 0;
+        if (e < e1) {
+          u_l = __ldg(a.col + e);
+          bits_l = __ldg(a.ebits + e) >> bbase;         // bit i: edge active in slot s_base + i
         }
-        dv = __ldg(a.scale + (int64_t)v * 32 + b);
-        for (int base = e0; base < e1; base += 32) {
-          int u_l = my_u;
-          uint32_t bits_l = my_bits;
-          if (base != e0) {
-            const int e = base + lane;
-            u_l = -1;
-            bits_l = 0;
-            if (e < e1) {
-              u_l = __ldg(a.col + e);
-              bits_l = __ldg(a.ebits + e);
-            }
-          }
-          uint32_t m = __ballot_sync(0xffffffffu, (bits_l >> b) & 1u);
-          while (m) {  // four independent 512-byte row gathers in flight per warp
-            int l[4];
-            bool on[4];
+        uint32_t m[8];
+        uint32_t any = 0;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              on[q] = m != 0;
-              l[q] = m ? __ffs(m) - 1 : 0;
-              m &= m - 1;
-            }
-            int u[4];
-            float kq[4];
-            float4 x[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) u[q] = __shfl_sync(0xffffffffu, u_l, l[q]);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              kq[q] = 0.f;
-              x[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (on[q]) {
-                kq[q] = a.kind == XPGNN_CONV_GCN ? __ldg(a.scale + (int64_t)u[q] * 32 + b) : 1.0f;
-                if (lane < k16) x[q] = __ldg(reinterpret_cast<const float4*>(in_s + (int64_t)u[q] * a.ld_in) + lane);
-              }
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              acc.x = fmaf(kq[q], x[q].x, acc.x);
-              acc.y = fmaf(kq[q], x[q].y, acc.y);
-              acc.z = fmaf(kq[q], x[q].z, acc.z);
-              acc.w = fmaf(kq[q], x[q].w, acc.w);
-            }
-          }
+        for (int i = 0; i < 8; ++i) {
+          m[i] = (s_base + i < a.n_bits) ? __ballot_sync(0xffffffffu, (bits_l >> i) & 1u) : 0u;
+          any |= m[i];
         }
-        if (a.kind == XPGNN_CONV_GCN) {
-          float4 self = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (lane < k16) self = __ldg(reinterpret_cast<const float4*>(in_s + (int64_t)v * a.ld_in) + lane);
-          acc.x = dv * fmaf(dv, self.x, acc.x);
-          acc.y = dv * fmaf(dv, self.y, acc.y);
-          acc.z = dv * fmaf(dv, self.z, acc.z);
-          acc.w = dv * fmaf(dv, self.w, acc.w);
-        } else {
-          acc.x *= dv; acc.y *= dv; acc.z *= dv; acc.w *= dv;
+        while (any) {
+          int u[8];
+          float kq[8];
+          float4 x[8];
+          any = 0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int l = m[i] ? __ffs(m[i]) - 1 : 0;
+            u[i] = __shfl_sync(0xffffffffu, u_l, l);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            kq[i] = 0.f;
+            x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m[i]) {
+              kq[i] = a.kind == XPGNN_CONV_GCN ? __ldg(a.scale + (int64_t)u[i] * 32 + bbase + i) : 1.0f;
+              if (lane < k16)
+                x[i] = __ldg(reinterpret_cast<const float4*>(a.in + (int64_t)(s_base + i) * a.in_s_stride + (int64_t)u[i] * a.ld_in) + lane);
+            }
+            m[i] &= m[i] - 1;
+            any |= m[i];
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            acc[i].x = fmaf(kq[i], x[i].x, acc[i].x);
+            acc[i].y = fmaf(kq[i], x[i].y, acc[i].y);
+            acc[i].z = fmaf(kq[i], x[i].z, acc[i].z);
+            acc[i].w = fmaf(kq[i], x[i].w, acc[i].w);
+          }
         }
       }
-      if (lane == 0) s_out_off[p] = valid ? (int64_t)s * a.out_s_stride + (int64_t)v * a.ld_out : -1;
-      if (lane < k16) {  // lane == sixteen-byte column of the row
-        float4 hi, lo;
-        hi.x = __uint_as_float(__float_as_uint(acc.x) & 0xffffe000u); lo.x = acc.x - hi.x;
-        hi.y = __uint_as_float(__float_as_uint(acc.y) & 0xffffe000u); lo.y = acc.y - hi.y;
-        hi.z = __uint_as_float(__float_as_uint(acc.z) & 0xffffe000u); lo.z = acc.z - hi.z;
-        hi.w = __uint_as_float(__float_as_uint(acc.w) & 0xffffe000u); lo.w = acc.w - hi.w;
-        const uint32_t off = (uint32_t)(p >> 3) * a_sbo + (uint32_t)lane * A_LBO + (uint32_t)(p & 7) * 16;
-        *reinterpret_cast<float4*>(sA + off) = hi;
-        *reinterpret_cast<float4*>(sA + a_part + off) = lo;
+      // finalise: normalisation (+ GCN self loop), TF32 hi/lo split, store to the A tile
+      float4 self[8];
+      float dv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const bool valid = row_ok && (s_base + i < a.n_bits);
+        dv[i] = valid ? __ldg(a.scale + (int64_t)v * 32 + bbase + i) : 0.f;
+        self[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid && a.kind == XPGNN_CONV_GCN && lane < k16)
+          self[i] = __ldg(reinterpret_cast<const float4*>(a.in + (int64_t)(s_base + i) * a.in_s_stride + (int64_t)v * a.ld_in) + lane);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int p = p0 + i;
+        const bool valid = row_ok && (s_base + i < a.n_bits);
+        float4 o;
+        if (a.kind == XPGNN_CONV_GCN) {
+          o.x = dv[i] * fmaf(dv[i], self[i].x, acc[i].x);
+          o.y = dv[i] * fmaf(dv[i], self[i].y, acc[i].y);
+          o.z = dv[i] * fmaf(dv[i], self[i].z, acc[i].z);
+          o.w = dv[i] * fmaf(dv[i], self[i].w, acc[i].w);
+        } else {
+          o.x = dv[i] * acc[i].x; o.y = dv[i] * acc[i].y; o.z = dv[i] * acc[i].z; o.w = dv[i] * acc[i].w;
+        }
+        if (lane == 0) s_out_off[p] = valid ? (int64_t)(s_base + i) * a.out_s_stride + (int64_t)v * a.ld_out : -1;
+        if (lane < k16) {  // lane == sixteen-byte column of the row
+          float4 hi, lo;
+          hi.x = __uint_as_float(__float_as_uint(o.x) & 0xffffe000u); lo.x = o.x - hi.x;
+          hi.y = __uint_as_float(__float_as_uint(o.y) & 0xffffe000u); lo.y = o.y - hi.y;
+          hi.z = __uint_as_float(__float_as_uint(o.z) & 0xffffe000u); lo.z = o.z - hi.z;
+          hi.w = __uint_as_float(__float_as_uint(o.w) & 0xffffe000u); lo.w = o.w - hi.w;
+          const uint32_t off = (uint32_t)(p >> 3) * a_sbo + (uint32_t)lane * A_LBO + (uint32_t)(p & 7) * 16;
+          *reinterpret_cast<float4*>(sA + off) = hi;
+          *reinterpret_cast<float4*>(sA + a_part + off) = lo;
+        }
       }
     }
     f_fence_proxy_async();
@@ -365,9 +371,9 @@ int fused_build_w_image(const float* w, int n_out, int K, float* img, cudaStream
 
 int launch_fused(FusedArgs a, cudaStream_t st) {
   a.n_pad = (a.n_out + 15) / 16 * 16;
-  int sb = 1;
+  int sb = 8;  // the 8 pairs of a warp must share a node row
   while (sb < a.n_bits && sb < 32) sb <<= 1;
-  if (a.SB <= 0) a.SB = sb;
+  if (a.SB < 8 || a.SB > 32 || (a.SB & (a.SB - 1))) a.SB = sb;
   const int k16 = a.K / 4;
   const size_t a_bytes = 2ull * 16 * k16 * A_LBO;
   const size_t t_bytes = (size_t)FM * 132 * 4;

@@ -259,11 +259,32 @@ def test_fused_spmm_dense_matches_oracle(hidden, lib, monkeypatch):
         ys[fused] = eng(act, s)[:, 0].cpu().numpy()
         np.testing.assert_allclose(ys[fused], y_ref.numpy().reshape(-1), rtol=Y_RTOL, atol=Y_ATOL)
     np.testing.assert_allclose(ys["1"], ys["0"], rtol=2e-5, atol=1e-6)
-    # coalition-major tiles (128 rows x 1 slot) and a memory-limited 8-coalition tile give the same numbers
+    # 8-slot tiles in coalition-major order and a memory-limited 8-coalition tile give the same numbers
     monkeypatch.setenv("XPGNN_FUSED", "1")
-    monkeypatch.setenv("XPGNN_FUSED_SB", "1")
+    monkeypatch.setenv("XPGNN_FUSED_SB", "8")
     eng = MaskedForward(GraphSpec(x.cuda(), ei.cuda(), [0, n]), lower(arch), [q], tile_coalitions=8)
     np.testing.assert_allclose(eng(act, s)[:, 0].cpu().numpy(), ys["1"], rtol=2e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("kind", ["gcn", "sage"])
+def test_bf16_transform_mode_within_tolerance(kind, lib):
+    """precision="bf16": dense transforms on tcgen05 with bf16 operands (fp32 accumulate, fp32 storage).
+    Bar from BASELINE.json north_star: predictions within 2e-2 relative."""
+    from bikg_graph_explainability_public_b200 import _lib
+    from bikg_graph_explainability_public_b200.engine import GraphSpec, MaskedForward
+    from bikg_graph_explainability_public_b200.lowering import lower
+    from oracle.xpgnn_oracle import kernel_output
+
+    x, ei, arch, mask, q = _random_model_case(5, kind, n=2000, e=16000, f=64, hidden=(64, 128), s=40)
+    s, n = mask.shape
+    _, y_ref = kernel_output(mask.numpy(), x, ei.numpy(), arch, q)
+    m8 = mask.to(torch.uint8).cuda().contiguous()
+    w = -(-s // 32)
+    act = torch.zeros((n, w), dtype=torch.int32, device="cuda")
+    _lib.check(lib.xpgnn_pack_mask(m8.data_ptr(), s, n, act.data_ptr(), w, None, _lib.stream_ptr()))
+    eng = MaskedForward(GraphSpec(x.cuda(), ei.cuda(), [0, n]), lower(arch), [q], precision="bf16")
+    y = eng(act, s)[:, 0].cpu().numpy()
+    np.testing.assert_allclose(y, y_ref.numpy().reshape(-1), rtol=2e-2, atol=2e-3)
 
 
 def test_wlm_fit_matches_closed_form(lib):
