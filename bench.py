@@ -281,7 +281,7 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     launches = _lib.launch_count() - launches0
-    prof_ms = (np.zeros(5), np.zeros(5, dtype=np.int64))
+    prof_ms = (np.zeros(6), np.zeros(6, dtype=np.int64))
     lib.xpgnn_profile_read(prof_ms[0].ctypes.data, prof_ms[1].ctypes.data)
     lib.xpgnn_profile(0)
 
@@ -304,7 +304,7 @@ def main():
         # algorithmic bytes of one coalition-layer: col idx + rowptr + bits + read Z once + write
         e_kept = eng.edges_per_layer[0]
         b_alg = 4 * e_kept + 4 * (n + 1) + n / 8 + 2 * n * h * 4
-        cats = ["masked_degree", "spmm_invariant_l0", "spmm_tile_l1", "dense", "head"]
+        cats = ["masked_degree", "spmm_invariant_l0", "spmm_tile_l1", "dense", "head", "compaction"]
         kern = {k: {"ms": float(prof_ms[0][i]), "launches": int(prof_ms[1][i])} for i, k in enumerate(cats)}
         peaks = {}
         try:

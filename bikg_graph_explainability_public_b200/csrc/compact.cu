@@ -1,0 +1,767 @@
+// Compact path of the coalition-batched masked message passing (homogeneous GCN / SAGE stacks, full mode).
+//
+// Same arithmetic as engine.cu (which replaces data.py:390-648 + model.py:62-328 of the reference), laid
+// out for the memory system of a B200:
+//
+//  1. A node that is inactive in coalition s has no active in-edge (edge (u->v) needs both endpoint bits),
+//     so its activation in every layer is the coalition-invariant "isolated node" value and no active
+//     edge ever gathers it.  Per coalition only the rows of ACTIVE nodes are computed and stored; the
+//     head evaluates the isolated chain itself when the query node is inactive.
+//  2. Per tile of <= 32 coalitions the active in-edges of every coalition are compacted once into a
+//     per-coalition CSR over its active rows (degree pass -> one CUB scan of packed (node, edge) counts ->
+//     list pass), shared by all conv layers.
+//  3. Activations are chunk-major, [chunk][node][CW] with CW = 32 floats (128 B): one (coalition, chunk)
+//     pass of the SpMM touches 64 MB at C3 (0.5 M active rows x 128 B) instead of 16 GB for a whole
+//     tile, so the ~10x re-gathers of every source row are served by the 126 MB L2 (measured with
+//     tools/gather_probe.cu: 11.3 TB/s from a 64 MB set vs 4.6 TB/s from 1 GB).
+//  4. GCN operands of layers >= 1 are stored pre-multiplied by deg^-1/2, so those gathers are
+//     unweighted sums; layer 0 gathers the coalition-invariant Z = X W^T with a per-source weight.
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <climits>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "engine_internal.cuh"
+
+namespace xpgnn {
+
+constexpr int kKeyShift = 36;  // packed scan key: active-node count << 36 | active in-edge count
+constexpr unsigned long long kEdgeMask = (1ull << kKeyShift) - 1ull;
+constexpr int kMaxConvIso = 8;
+constexpr int kMaxHeadC = 8;
+
+// ------------------------------------------------------------------------------------------
+// pass 1: edge-activity words of the coalition word + packed per-(coalition, node) counts
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) compact_degree_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                             const uint32_t* __restrict__ act, int W, int w, int b0, int nb, int N,
+                                                             uint32_t* __restrict__ ebits, unsigned long long* __restrict__ keys,
+                                                             float* __restrict__ scale, int kind) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  for (int v = blockIdx.x * wpb + wib; v < N; v += gridDim.x * wpb) {
+    const int e0 = rowptr[v], e1 = rowptr[v + 1];
+    const uint32_t av = act[(int64_t)v * W + w];
+    int cnt = 0;
+    for (int base = e0; base < e1; base += 32) {
+      const int e = base + lane;
+      uint32_t bits = 0;
+      if (e < e1) {
+        bits = act[(int64_t)col[e] * W + w] & av;
+        ebits[e] = bits;
+      }
+      const int n = min(32, e1 - base);
+      for (int j = 0; j < n; ++j) cnt += (__shfl_sync(0xffffffffu, bits, j) >> lane) & 1u;
+    }
+    // [N][32] by bit of the word: GCN (1 + masked in-degree)^-1/2, SAGE 1 / max(1, masked in-degree)
+    if (scale) scale[(int64_t)v * 32 + lane] = kind == XPGNN_CONV_GCN ? gcn_dinv((uint32_t)cnt) : 1.0f / (float)max(cnt, 1);
+    const int t = lane - b0;  // lane = bit of the word, t = slot of the tile
+    if (t >= 0 && t < nb) keys[(int64_t)t * N + v] = ((av >> lane) & 1u) ? ((1ull << kKeyShift) | (unsigned long long)cnt) : 0ull;
+  }
+}
+
+// pass 2 (after the exclusive scan of the keys): per-coalition list of active rows, compact in-edge
+// offsets, per-source GCN weight of layer 0, per-slot totals
+__global__ void __launch_bounds__(256) compact_finalize_kernel(const unsigned long long* __restrict__ keys,
+                                                               const unsigned long long* __restrict__ scanned, int N,
+                                                               int32_t* __restrict__ act_list, uint32_t* __restrict__ rowptr_c,
+                                                               float* __restrict__ wgt, int2* __restrict__ slot_info,
+                                                               long long* __restrict__ slot_base) {
+  const int t = blockIdx.y;
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= N) return;
+  const int64_t g = (int64_t)t * N + v;
+  const unsigned long long K = keys[g], S = scanned[g], B = scanned[(int64_t)t * N];
+  if (K >> kKeyShift) {
+    const int64_t i = (int64_t)((S >> kKeyShift) - (B >> kKeyShift));
+    act_list[(int64_t)t * N + i] = v;
+    rowptr_c[(int64_t)t * (N + 1) + i] = (uint32_t)((S & kEdgeMask) - (B & kEdgeMask));
+  }
+  if (wgt) wgt[g] = gcn_dinv((uint32_t)(K & kEdgeMask));
+  if (v == N - 1) {
+    const unsigned long long T = S + K;
+    const int n_act = (int)((T >> kKeyShift) - (B >> kKeyShift));
+    const unsigned long long tot = (T & kEdgeMask) - (B & kEdgeMask);
+    rowptr_c[(int64_t)t * (N + 1) + n_act] = (uint32_t)tot;
+    slot_info[t] = make_int2(n_act, (int)min(tot, (unsigned long long)INT_MAX));
+    slot_base[t] = (long long)(B & kEdgeMask);
+  }
+}
+
+// 128-row tiles of every slot's active-row list (the dense transform's work list) + stats
+__global__ void __launch_bounds__(256) compact_tilemap_kernel(const int2* __restrict__ slot_info, int nb, int32_t* __restrict__ slot_tile_start,
+                                                              int32_t* __restrict__ n_tiles, int2* __restrict__ tile_map, int n_layers,
+                                                              int64_t* stats, int32_t* __restrict__ counters) {
+  __shared__ int start[33];
+  if (threadIdx.x < 16) counters[threadIdx.x] = 0;  // work counters of the SpMM launches of this tile
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    long long active = 0;
+    for (int t = 0; t < nb; ++t) {
+      start[t] = acc;
+      acc += (slot_info[t].x + 127) / 128;
+      active += slot_info[t].y;
+    }
+    start[nb] = acc;
+    *n_tiles = acc;
+    if (stats) {
+      stats[1] += active * n_layers;
+      stats[3] += 1;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x <= nb) slot_tile_start[threadIdx.x] = start[threadIdx.x];
+  for (int t = 0; t < nb; ++t)
+    for (int k = threadIdx.x; k < start[t + 1] - start[t]; k += blockDim.x) tile_map[start[t] + k] = make_int2(t, k * 128);
+}
+
+// pass 3: per-coalition compacted source lists (original node ids, CSR order kept)
+__global__ void __launch_bounds__(256) compact_edges_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                            const uint32_t* __restrict__ ebits, const uint32_t* __restrict__ act, int W,
+                                                            int w, int b0, int nb, int N, const unsigned long long* __restrict__ scanned,
+                                                            int32_t* __restrict__ ccol) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const uint32_t tile_mask = nb == 32 ? 0xffffffffu : ((1u << nb) - 1u);
+  const uint32_t lt = (1u << lane) - 1u;
+  for (int v = blockIdx.x * wpb + wib; v < N; v += gridDim.x * wpb) {
+    const uint32_t av = (act[(int64_t)v * W + w] >> b0) & tile_mask;
+    if (!av) continue;
+    const int e0 = rowptr[v], e1 = rowptr[v + 1];
+    if (e0 == e1) continue;
+    unsigned long long base = 0;  // lane t: write cursor of slot t (offset into the concatenated lists)
+    if ((av >> lane) & 1u) base = scanned[(int64_t)lane * N + v] & kEdgeMask;
+    for (int b = e0; b < e1; b += 32) {
+      const int e = b + lane;
+      int u = -1;
+      uint32_t bits = 0;
+      if (e < e1) {
+        u = __ldg(col + e);
+        bits = (__ldg(ebits + e) >> b0) & tile_mask;
+      }
+      uint32_t rem = __reduce_or_sync(0xffffffffu, bits);  // slots with an active edge in this batch
+      while (rem) {
+        const int t = __ffs(rem) - 1;
+        rem &= rem - 1;
+        const uint32_t m = __ballot_sync(0xffffffffu, (bits >> t) & 1u);
+        const unsigned long long bt = __shfl_sync(0xffffffffu, base, t);
+        if ((bits >> t) & 1u) ccol[bt + __popc(m & lt)] = u;
+        if (lane == t) base += __popc(m);
+      }
+    }
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// layer 0, row-outer: the gathered operand Z = X W^T is coalition invariant, so a neighbour row crosses
+// the L2 fabric ONCE per destination row and is reused from registers for every coalition slot of the tile
+// (the list-driven kernel below moves it once per (slot, edge): 82 GB per C3 tile against ~12 GB here).
+// ------------------------------------------------------------------------------------------
+struct L0RowsArgs {
+  const int32_t* rowptr;
+  const int32_t* col;
+  const uint32_t* ebits;
+  const uint32_t* act;
+  int W, w, b0, nb, N;
+  const float* scale;        // [N][32] by bit of the word
+  const float* z;            // [N][h0] row-major
+  int h0;
+  const float* bias;         // GCN bias or NULL
+  const float* r0c;          // SAGE: b + X W_root^T, chunk-major (cw = 32) or NULL
+  int64_t r0_chunk_stride;
+  float* out;                // chunk-major (cw = 32) activations of the tile
+  int64_t out_s_stride, out_chunk_stride;
+  int kind, act_fn, prescale;
+};
+
+constexpr int kL0WStride = 36;  // floats per staged weight row (32 + pad: 16-byte aligned, 4-way instead of 32-way store conflicts)
+constexpr int kL0SmemBytes = 8 * 32 * kL0WStride * 4 + 8 * 32 * 64 * 4 + 8 * 32 * 4;
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// A warp owns one destination row and walks its 64-column blocks; a lane owns 2 columns of the block and
+// the accumulators of ALL 32 bits of the coalition word (64 registers).  Per batch of <= 32 in-edges:
+//   weights : lane j loads the 32 per-slot scales of source u_j (8 independent 128-bit loads), zeroes the
+//             slots in which edge j is inactive and stores the row to shared memory (once per row);
+//   operand : the 256-byte pieces of Z[u_j] go to shared memory with cp.async, all in flight together;
+//   FMAs    : per edge 1 LDS.64 (z) + 8 broadcast LDS.128 (weights) + 64 FFMA, unconditional.
+template <bool SIGMOID>
+__global__ void __launch_bounds__(256, 2) l0_rows_kernel(const L0RowsArgs a) {
+  extern __shared__ __align__(16) uint8_t l0_smem[];
+  float(*s_w)[32][kL0WStride] = reinterpret_cast<float(*)[32][kL0WStride]>(l0_smem);
+  float(*s_z)[32][64] = reinterpret_cast<float(*)[32][64]>(l0_smem + 8 * 32 * kL0WStride * 4);
+  int(*s_u)[32] = reinterpret_cast<int(*)[32]>(l0_smem + 8 * 32 * kL0WStride * 4 + 8 * 32 * 64 * 4);
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t live = (a.nb == 32 ? 0xffffffffu : ((1u << a.nb) - 1u)) << a.b0;  // bits of the word in this tile
+  const bool gcn = a.kind == XPGNN_CONV_GCN;
+  const int ncb = a.h0 / 64;
+  for (int v = blockIdx.x * 8 + wib; v < a.N; v += gridDim.x * 8) {
+    const uint32_t av = a.act[(int64_t)v * a.W + a.w] & live;
+    if (!av) continue;
+    const int e0 = a.rowptr[v], e1 = a.rowptr[v + 1];
+    const bool short_row = e1 - e0 <= 32;
+    const float sc_v = a.scale[(int64_t)v * 32 + lane];
+    for (int cb = 0; cb < ncb; ++cb) {
+      const float* zc = a.z + cb * 64 + lane * 2;
+      float2 acc[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) acc[k] = make_float2(0.f, 0.f);
+      for (int base = e0; base < e1; base += 32) {
+        const int n = min(32, e1 - base);
+        __syncwarp();
+        if (cb == 0 || !short_row) {  // weights of the batch (kept across column blocks for short rows)
+          if (lane < n) {
+            const int u = __ldg(a.col + base + lane);
+            const uint32_t bits = __ldg(a.ebits + base + lane) & av;
+            s_u[wib][lane] = u;
+            float4 wq[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              wq[q] = gcn ? __ldg(reinterpret_cast<const float4*>(a.scale + (int64_t)u * 32 + q * 4)) : make_float4(1.f, 1.f, 1.f, 1.f);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              wq[q].x = (bits >> (4 * q + 0)) & 1u ? wq[q].x : 0.0f;
+              wq[q].y = (bits >> (4 * q + 1)) & 1u ? wq[q].y : 0.0f;
+              wq[q].z = (bits >> (4 * q + 2)) & 1u ? wq[q].z : 0.0f;
+              wq[q].w = (bits >> (4 * q + 3)) & 1u ? wq[q].w : 0.0f;
+              *reinterpret_cast<float4*>(&s_w[wib][lane][4 * q]) = wq[q];
+            }
+          }
+          __syncwarp();
+        }
+#pragma unroll 4
+        for (int j = 0; j < n; ++j) cp_async8(&s_z[wib][j][lane * 2], zc + (int64_t)s_u[wib][j] * a.h0);
+        cp_async_wait_all();
+        __syncwarp();
+#pragma unroll 1
+        for (int j = 0; j < n; ++j) {
+          const float2 zv = *reinterpret_cast<const float2*>(&s_z[wib][j][lane * 2]);
+          const float4* wr = reinterpret_cast<const float4*>(&s_w[wib][j][0]);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 w4 = wr[q];
+            acc[4 * q + 0].x = fmaf(w4.x, zv.x, acc[4 * q + 0].x); acc[4 * q + 0].y = fmaf(w4.x, zv.y, acc[4 * q + 0].y);
+            acc[4 * q + 1].x = fmaf(w4.y, zv.x, acc[4 * q + 1].x); acc[4 * q + 1].y = fmaf(w4.y, zv.y, acc[4 * q + 1].y);
+            acc[4 * q + 2].x = fmaf(w4.z, zv.x, acc[4 * q + 2].x); acc[4 * q + 2].y = fmaf(w4.z, zv.y, acc[4 * q + 2].y);
+            acc[4 * q + 3].x = fmaf(w4.w, zv.x, acc[4 * q + 3].x); acc[4 * q + 3].y = fmaf(w4.w, zv.y, acc[4 * q + 3].y);
+          }
+        }
+      }
+      // ---- epilogue of the column block ----
+      float2 self = make_float2(0.f, 0.f), add = self;
+      if (gcn) self = __ldg(reinterpret_cast<const float2*>(zc + (int64_t)v * a.h0));
+      const int64_t cm_off = (int64_t)(cb * 2 + (lane >> 4)) * a.out_chunk_stride + (int64_t)v * 32 + (lane & 15) * 2;
+      if (a.bias) add = __ldg(reinterpret_cast<const float2*>(a.bias + cb * 64 + lane * 2));
+      if (a.r0c) {
+        const float2 r = __ldg(reinterpret_cast<const float2*>(a.r0c + (int64_t)(cb * 2 + (lane >> 4)) * a.r0_chunk_stride + (int64_t)v * 32 + (lane & 15) * 2));
+        add.x += r.x; add.y += r.y;
+      }
+      // the 32-fold unrolled epilogue is kept tiny (the whole kernel must stay inside the instruction cache):
+      // GCN and SAGE share one formula (SAGE: self = 0), ReLU / identity are a max with 0 / -inf
+      const float lower = a.act_fn == XPGNN_ACT_RELU ? 0.0f : -INFINITY;
+      float* outp = a.out + cm_off - (int64_t)a.b0 * a.out_s_stride;
+#pragma unroll
+      for (int k = 0; k < 32; ++k, outp += a.out_s_stride) {
+        const float dv = __shfl_sync(0xffffffffu, sc_v, k);
+        if ((av >> k) & 1u) {  // warp uniform
+          const float pv = a.prescale ? dv : 1.0f;
+          float2 o;
+          o.x = dv * fmaf(self.x, gcn ? dv : 0.0f, acc[k].x) + add.x;
+          o.y = dv * fmaf(self.y, gcn ? dv : 0.0f, acc[k].y) + add.y;
+          if (SIGMOID) {
+            o.x = apply_act(o.x, XPGNN_ACT_SIGMOID); o.y = apply_act(o.y, XPGNN_ACT_SIGMOID);
+          } else {
+            o.x = fmaxf(o.x, lower); o.y = fmaxf(o.y, lower);
+          }
+          o.x *= pv; o.y *= pv;
+          __stcs(reinterpret_cast<float2*>(outp), o);
+        }
+      }
+    }
+  }
+}
+
+// ---- L2 eviction-priority hints (createpolicy + .L2::cache_hint): the (slot, chunk) pass wants its gathered
+// operand to own the L2; index streams, the self / addend rows and the output are touched once ----
+__device__ __forceinline__ uint64_t l2_policy(int kind /*0 normal, 1 evict_first, 2 evict_last*/) {
+  uint64_t p;
+  if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ int ld_hint(const int32_t* ptr, uint64_t pol) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(ptr), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_hint(const uint32_t* ptr, uint64_t pol) {
+  uint32_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(ptr), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float4 ld_hint4(const float* ptr, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void st_hint4(float* ptr, const float4& v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// masked SpMM over the compact lists: work item = (coalition slot, chunk, 128 active rows), items
+// ordered slot-major / chunk / tile and dealt round-robin to a persistent grid, so that at any time
+// the whole GPU works on one (slot, chunk) pass (+- skew) whose gathered operand fits in L2.
+// A row is owned by CW/4 lanes (float4 each); a warp advances 32/(CW/4) rows together.
+// ------------------------------------------------------------------------------------------
+struct CspmmArgs {
+  int nb, N, n_chunks, kind, layer0, act_fn, prescale;
+  const int2* slot_info;
+  const int32_t* slot_tile_start;
+  const int32_t* act_list;    // [nb][N]
+  const uint32_t* rowptr_c;   // [nb][N+1]
+  const long long* slot_base; // [nb] first entry of the slot's list in ccol
+  const int32_t* ccol;
+  const float* in;            // chunk-major operand, rows by original node id
+  int64_t in_s_stride;        // 0: coalition invariant (layer 0)
+  int64_t in_chunk_stride;
+  const float* wgt;           // [nb][N] per-source weight (layer-0 GCN) or NULL
+  const float* addend;        // chunk-major coalition-invariant addend or NULL
+  int64_t add_chunk_stride;
+  const float* bias;          // per-column addend or NULL
+  int32_t* counter;           // work counter (zeroed per launch); NULL: static round-robin
+  int l2_stream, l2_gather;   // eviction priority of the streamed / gathered accesses (l2_policy kinds)
+  float* out;
+  int64_t out_s_stride, out_chunk_stride;
+};
+
+template <int CW, bool WEIGHTED, int OCC>
+__global__ void __launch_bounds__(256, OCC) cspmm_kernel(const CspmmArgs a) {
+  constexpr int G = CW / 4;        // lanes per row
+  constexpr int RPW = 32 / G;      // rows per warp
+  constexpr int RPI = 8 * RPW;     // rows per CTA iteration
+  constexpr int ITERS = 128 / RPI;
+  __shared__ int s_start[33];
+  __shared__ int s_item;
+  if (threadIdx.x <= a.nb) s_start[threadIdx.x] = a.slot_tile_start[threadIdx.x];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane % G, grp = lane / G;
+  const int total = s_start[a.nb] * a.n_chunks;
+  const uint64_t pol_s = l2_policy(a.l2_stream), pol_g = l2_policy(a.l2_gather);
+  int t = 0;
+  int idx = blockIdx.x;
+  while (true) {
+    if (a.counter) {  // items are handed out in global order: the in-flight window is one grid wide
+      if (threadIdx.x == 0) s_item = atomicAdd(a.counter, 1);
+      __syncthreads();
+      idx = s_item;
+      __syncthreads();
+    }
+    if (idx >= total) break;
+    while (idx >= s_start[t + 1] * a.n_chunks) ++t;
+    const int ntb = s_start[t + 1] - s_start[t];
+    const int rem = idx - s_start[t] * a.n_chunks;
+    const int c = rem / ntb, tb = rem - c * ntb;
+    const int n_act = a.slot_info[t].x;
+    const int32_t* al = a.act_list + (int64_t)t * a.N;
+    const uint32_t* rp = a.rowptr_c + (int64_t)t * (a.N + 1);
+    const int32_t* cc = a.ccol + a.slot_base[t];
+    const float* in_c = a.in + (int64_t)t * a.in_s_stride + (int64_t)c * a.in_chunk_stride + sub * 4;
+    const float* wg = WEIGHTED ? a.wgt + (int64_t)t * a.N : nullptr;
+    float* out_c = a.out + (int64_t)t * a.out_s_stride + (int64_t)c * a.out_chunk_stride + sub * 4;
+    const float* add_c = a.addend ? a.addend + (int64_t)c * a.add_chunk_stride + sub * 4 : nullptr;
+    float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.bias) bias = __ldg(reinterpret_cast<const float4*>(a.bias + c * CW + sub * 4));
+#pragma unroll 1
+    for (int it = 0; it < ITERS; ++it) {
+      const int i = tb * 128 + it * RPI + warp * RPW + grp;
+      const bool valid = i < n_act;
+      int v = 0;
+      uint32_t e0 = 0, cnt = 0;
+      if (valid) {  // streaming reads: keep the L2 for the gathered operand
+        v = ld_hint(al + i, pol_s);
+        e0 = ld_hint(rp + i, pol_s);
+        cnt = ld_hint(rp + i + 1, pol_s) - e0;
+      }
+      const uint32_t maxcnt = __reduce_max_sync(0xffffffffu, cnt);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (uint32_t base = 0; base < maxcnt; base += G) {
+        int my = -1;
+        float myw = 0.f;
+        if (base + sub < cnt) {
+          my = ld_hint(cc + e0 + base + sub, pol_s);
+          if (WEIGHTED) myw = __ldg(wg + my);
+        }
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+          const int u = __shfl_sync(0xffffffffu, my, grp * G + j);
+          const float wj = WEIGHTED ? __shfl_sync(0xffffffffu, myw, grp * G + j) : 1.0f;
+          if (u >= 0) {
+            const float4 x = ld_hint4(in_c + (int64_t)u * CW, pol_g);
+            acc.x = fmaf(wj, x.x, acc.x); acc.y = fmaf(wj, x.y, acc.y);
+            acc.z = fmaf(wj, x.z, acc.z); acc.w = fmaf(wj, x.w, acc.w);
+          }
+        }
+      }
+      if (valid) {
+        float4 o;
+        float dinv = 1.0f;
+        if (a.kind == XPGNN_CONV_GCN) {
+          dinv = gcn_dinv(cnt);
+          const float4 self = ld_hint4(in_c + (int64_t)v * CW, pol_g);
+          const float sw = a.layer0 ? dinv : 1.0f;  // layers >= 1 gather operands already scaled by deg^-1/2
+          o.x = dinv * fmaf(sw, self.x, acc.x); o.y = dinv * fmaf(sw, self.y, acc.y);
+          o.z = dinv * fmaf(sw, self.z, acc.z); o.w = dinv * fmaf(sw, self.w, acc.w);
+        } else {
+          const float inv = 1.0f / (float)max(cnt, 1u);
+          o.x = acc.x * inv; o.y = acc.y * inv; o.z = acc.z * inv; o.w = acc.w * inv;
+        }
+        o.x += bias.x; o.y += bias.y; o.z += bias.z; o.w += bias.w;
+        if (add_c) {
+          const float4 ad = ld_hint4(add_c + (int64_t)v * CW, pol_s);
+          o.x += ad.x; o.y += ad.y; o.z += ad.z; o.w += ad.w;
+        }
+        o.x = apply_act(o.x, a.act_fn); o.y = apply_act(o.y, a.act_fn);
+        o.z = apply_act(o.z, a.act_fn); o.w = apply_act(o.w, a.act_fn);
+        if (a.prescale) { o.x *= dinv; o.y *= dinv; o.z *= dinv; o.w *= dinv; }
+        st_hint4(out_c + (int64_t)v * CW, o, pol_s);
+      }
+    }
+    if (!a.counter) idx += gridDim.x;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// head on the query rows; an inactive query takes the isolated-node chain (coalition invariant)
+// ------------------------------------------------------------------------------------------
+struct CHeadArgs {
+  int n_iso;                        // conv layers >= 1 of the isolated chain: x = act(W x + b)
+  xpgnn_dense_t iso[kMaxConvIso];
+  int kind0, act0, h0;              // layer 0 of the isolated chain: GCN act(R0[q] + Z[q]) | SAGE act(R0[q])
+  const float* zc;                  // Z = X W^T, chunk-major or (z_rowmajor) [N][h0]
+  int z_rowmajor;
+  const float* r0c;                 // SAGE: b + X W_root^T (chunk-major) | NULL
+  const float* bias0;               // GCN: bias vector | NULL
+  int64_t z_chunk_stride;
+  int n_head;
+  xpgnn_dense_t head[kMaxHeadC];
+  const float* in;                  // last conv output, chunk-major
+  int64_t in_s_stride, in_chunk_stride;
+  int dim0, cw, cw_lg;
+  const int32_t* query;
+  int n_query, out_col;
+  float* y;                         // y[slot * n_query + q]
+  const uint32_t* act;
+  int W, w, b0;
+};
+
+__device__ __forceinline__ void head_dense(const xpgnn_dense_t& L, const float* x0, float* x1) {
+  for (int n = threadIdx.x; n < L.out; n += blockDim.x) {
+    float s = 0.0f;
+    const float* wr = L.w + (int64_t)n * L.in;
+    if (L.w)
+      for (int k = 0; k < L.in; ++k) s = fmaf(x0[k], __ldg(wr + k), s);
+    if (L.b) s += __ldg(L.b + n);
+    x1[n] = apply_act(s, L.act);
+  }
+}
+
+__global__ void __launch_bounds__(128) compact_head_kernel(const CHeadArgs a, int max_dim) {
+  extern __shared__ float sm[];
+  float* x0 = sm;
+  float* x1 = sm + max_dim;
+  const int slot = blockIdx.x / a.n_query, q = blockIdx.x % a.n_query;
+  const int qv = a.query[q];
+  const bool active = (a.act[(int64_t)qv * a.W + a.w] >> (a.b0 + slot)) & 1u;
+  if (active) {
+    const float* src = a.in + (int64_t)slot * a.in_s_stride + (int64_t)qv * a.cw;
+    for (int i = threadIdx.x; i < a.dim0; i += blockDim.x) x0[i] = src[(int64_t)(i >> a.cw_lg) * a.in_chunk_stride + (i & (a.cw - 1))];
+    __syncthreads();
+  } else {
+    for (int i = threadIdx.x; i < a.h0; i += blockDim.x) {
+      const int64_t off = (int64_t)(i >> a.cw_lg) * a.z_chunk_stride + (int64_t)qv * a.cw + (i & (a.cw - 1));
+      const float zq = a.kind0 == XPGNN_CONV_GCN ? (a.z_rowmajor ? a.zc[(int64_t)qv * a.h0 + i] : a.zc[off]) : 0.0f;
+      const float r = (a.r0c ? a.r0c[off] : 0.0f) + (a.bias0 ? a.bias0[i] : 0.0f) + zq;
+      x0[i] = apply_act(r, a.act0);
+    }
+    __syncthreads();
+    for (int li = 0; li < a.n_iso; ++li) {
+      head_dense(a.iso[li], x0, x1);
+      __syncthreads();
+      float* tp = x0; x0 = x1; x1 = tp;
+    }
+  }
+  for (int li = 0; li < a.n_head; ++li) {
+    head_dense(a.head[li], x0, x1);
+    __syncthreads();
+    float* tp = x0; x0 = x1; x1 = tp;
+  }
+  if (threadIdx.x == 0) a.y[(int64_t)slot * a.n_query + q] = x0[a.out_col];
+}
+
+// ------------------------------------------------------------------------------------------ host
+static bool compact_enabled() {
+  const char* e = getenv("XPGNN_COMPACT");
+  return !(e && std::string(e) == "0");
+}
+
+static int compact_cw(const xpgnn_plan_t* p) {
+  const char* e = getenv("XPGNN_CW");
+  int cw = 32;
+  if (e && atoi(e) == 16) cw = 16;
+  for (int l = 0; l < p->n_layers; ++l)
+    if (p->layers_host[l].h_out % cw) cw = 16;
+  return cw;
+}
+
+bool compact_eligible(const xpgnn_plan_t* p) {
+  if (!compact_enabled() || p->prune || p->zero_edge_rule || p->n_layers < 1 || p->n_layers > std::min(kMaxConvIso, 16)) return false;
+  if (p->n_head > kMaxHeadC) return false;
+  const xpgnn_relation_t& R0 = p->layers_host[0].rel_host[0];
+  for (int l = 0; l < p->n_layers; ++l) {
+    const xpgnn_layer_t& L = p->layers_host[l];
+    if (L.n_rel != 1 || L.h_out % 16) return false;
+    const xpgnn_relation_t& R = L.rel_host[0];
+    if (R.src_lo != 0 || R.src_hi != p->n_nodes || R.dst_lo != 0 || R.dst_hi != p->n_nodes) return false;
+    if (R.rowptr != R0.rowptr || R.col != R0.col || R.conv_kind != R0.conv_kind) return false;
+    if (l > 0 && L.h_in != p->layers_host[l - 1].h_out) return false;
+  }
+  return true;
+}
+
+struct CLayout {
+  float *zc, *r0c;
+  uint32_t* ebits;
+  unsigned long long *keys, *scanned;
+  void* cub_tmp;
+  size_t cub_bytes;
+  int32_t* act_list;
+  uint32_t* rowptr_c;
+  float* wgt;
+  float* scale;
+  int2* slot_info;
+  long long* slot_base;
+  int32_t *slot_tile_start, *n_tiles, *counters;
+  int2* tile_map;
+  int32_t* ccol;
+  float *hbuf[2], *agg;
+  int64_t bytes;
+};
+
+static CLayout compact_carve(const xpgnn_plan_t* p, void* ws, int64_t cap, int tile) {
+  CLayout c{};
+  Bump b(ws, cap);
+  const int64_t N = p->n_nodes, E = std::max(p->layers_host[0].rel_host[0].n_edges, 1);
+  const int NL = p->n_layers;
+  int hmax = 0;
+  for (int l = 0; l < NL; ++l) hmax = std::max(hmax, p->layers_host[l].h_out);
+  const int h0 = p->layers_host[0].h_out;
+  c.zc = b.take<float>(N * h0);
+  c.r0c = b.take<float>(N * h0);
+  c.ebits = b.take<uint32_t>(E);
+  c.keys = b.take<unsigned long long>((int64_t)tile * N + 1);
+  c.scanned = b.take<unsigned long long>((int64_t)tile * N + 1);
+  c.cub_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, c.cub_bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (int64_t)tile * N + 1);
+  c.cub_tmp = b.take<char>((int64_t)c.cub_bytes + 256);
+  c.act_list = b.take<int32_t>((int64_t)tile * N);
+  c.rowptr_c = b.take<uint32_t>((int64_t)tile * (N + 1));
+  c.wgt = b.take<float>((int64_t)tile * N);
+  c.scale = b.take<float>(N * 32);
+  c.slot_info = b.take<int2>(32);
+  c.slot_base = b.take<long long>(32);
+  c.slot_tile_start = b.take<int32_t>(33);
+  c.n_tiles = b.take<int32_t>(1);
+  c.counters = b.take<int32_t>(16);
+  c.tile_map = b.take<int2>((int64_t)tile * ceil_div(N, 128));
+  c.ccol = b.take<int32_t>((int64_t)tile * E);
+  c.hbuf[0] = b.take<float>((int64_t)tile * N * hmax);
+  if (NL > 1) {
+    c.hbuf[1] = b.take<float>((int64_t)tile * N * hmax);
+    c.agg = b.take<float>((int64_t)tile * N * hmax);
+  }
+  c.bytes = (b.off + 255) & ~255ll;
+  return c;
+}
+
+int64_t compact_workspace_bytes(const xpgnn_plan_t* p, int tile) { return compact_carve(p, nullptr, 0, tile).bytes; }
+
+static int launch_cspmm(const CspmmArgs& a, int cw, cudaStream_t st) {
+  const int occ = getenv("XPGNN_OCC") ? atoi(getenv("XPGNN_OCC")) : 8;
+  void (*k)(const CspmmArgs);
+  if (occ >= 8)
+    k = cw == 32 ? (a.wgt ? cspmm_kernel<32, true, 8> : cspmm_kernel<32, false, 8>) : (a.wgt ? cspmm_kernel<16, true, 8> : cspmm_kernel<16, false, 8>);
+  else
+    k = cw == 32 ? (a.wgt ? cspmm_kernel<32, true, 6> : cspmm_kernel<32, false, 6>) : (a.wgt ? cspmm_kernel<16, true, 6> : cspmm_kernel<16, false, 6>);
+  // every CTA must be resident: the round-robin deal of the items keeps the whole grid inside one
+  // (slot, chunk) pass only if no CTA starts late
+  int per_sm = 0;
+  XP_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, 256, 0));
+  const int grid = kNumSMs * std::max(per_sm, 1);
+  ProfScope ps(a.layer0 ? PROF_SPMM_INVARIANT : PROF_SPMM_TILE, st);
+  XP_LAUNCH(k, grid, 256, 0, st, a);
+  return 0;
+}
+
+int forward_compact(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32_t s0, int32_t n_s, float* y, void* workspace,
+                    int64_t workspace_bytes, int64_t* stats, cudaStream_t st, int dense_prec) {
+  const int N = p->n_nodes, NL = p->n_layers;
+  const xpgnn_relation_t& R0 = p->layers_host[0].rel_host[0];
+  const int kind = R0.conv_kind;
+  const int cw = compact_cw(p), cw_lg = cw == 32 ? 5 : 4;
+  int tile = 32;
+  while (tile > 1 && compact_carve(p, nullptr, 0, tile).bytes > workspace_bytes) tile >>= 1;
+  XP_REQUIRE(compact_carve(p, nullptr, 0, tile).bytes <= workspace_bytes, "workspace too small even for one coalition per tile");
+  XP_REQUIRE((int64_t)tile * std::max(R0.n_edges, 1) < (1ll << kKeyShift), "tile x edges exceeds the packed scan key");
+  CLayout lay = compact_carve(p, workspace, workspace_bytes, tile);
+  int hmax = 0;
+  for (int l = 0; l < NL; ++l) hmax = std::max(hmax, p->layers_host[l].h_out);
+  const int64_t hstride = (int64_t)N * hmax;       // per-slot stride of the activation buffers
+  const int64_t cstride = (int64_t)N * cw;         // chunk stride
+
+  // ---- coalition-invariant part of layer 0: Z = X W^T, R0 = b (+ X W_root^T for SAGE) ----
+  const xpgnn_layer_t& L0 = p->layers_host[0];
+  XP_REQUIRE(L0.h_in == p->f_in, "layer 0 input width != feature width");
+  // row-outer layer 0 (Z row-major) when a warp can own 128 columns; else the list-driven kernel (Z chunk-major)
+  const bool l0_lists = getenv("XPGNN_L0") && std::string(getenv("XPGNN_L0")) == "lists";
+  const bool l0_rows = !l0_lists && cw == 32 && L0.h_out % 64 == 0;
+  {
+    DenseArgs z{};
+    z.in = p->x; z.ld_in = p->f_in; z.k = p->f_in; z.w = R0.w_nbr; z.n_out = L0.h_out; z.out = lay.zc;
+    z.ld_out = cw; z.cw_out = cw; z.cw_out_lg = cw_lg; z.out_chunk_stride = cstride;
+    z.rows_per_s = N; z.row_lo = 0; z.M = N; z.dst_lo = 0; z.dst_hi = N;
+    DenseArgs zz = z;
+    if (l0_rows) { zz.ld_out = L0.h_out; zz.cw_out = 0; zz.cw_out_lg = 0; zz.out_chunk_stride = 0; }
+    if (launch_dense(zz, st, dense_prec)) return 1;
+    if (kind == XPGNN_CONV_SAGE_MEAN) {  // GCN only adds its bias vector (in the SpMM epilogue)
+      const bool sage_root = R0.w_root != nullptr;
+      DenseArgs rt = z;  // k = 0 degenerates to "write the bias"
+      rt.k = sage_root ? p->f_in : 0; rt.w = sage_root ? R0.w_root : R0.w_nbr; rt.b = R0.b_nbr; rt.out = lay.r0c;
+      if (launch_dense(rt, st, dense_prec)) return 1;
+    }
+  }
+  const int l2_stream = getenv("XPGNN_L2_STREAM") ? atoi(getenv("XPGNN_L2_STREAM")) : 1;
+  const int l2_gather = getenv("XPGNN_L2_GATHER") ? atoi(getenv("XPGNN_L2_GATHER")) : 0;
+  const bool dyn_sched = !(getenv("XPGNN_SCHED") && std::string(getenv("XPGNN_SCHED")) == "static");
+  XP_CHECK(cudaMemsetAsync(lay.keys + (int64_t)tile * N, 0, sizeof(unsigned long long), st));
+
+  const int w_first = s0 / 32, w_last = (s0 + n_s - 1) / 32;
+  const int grid_rows = (int)std::min<int64_t>(std::max<int64_t>(ceil_div(N, 8), 1), (int64_t)kNumSMs * 8);
+  for (int w = w_first; w <= w_last; ++w) {
+    const int bits_in_word = std::min(32, s0 + n_s - w * 32);
+    for (int b0 = 0; b0 < bits_in_word; b0 += tile) {
+      const int nb = std::min(tile, bits_in_word - b0);
+      // ---- per-tile compaction ----
+      {
+        ProfScope ps(PROF_SCALE, st);
+        XP_LAUNCH(compact_degree_kernel, grid_rows, 256, 0, st, R0.rowptr, R0.col, act, W, w, b0, nb, N, lay.ebits, lay.keys,
+                  l0_rows ? lay.scale : nullptr, kind);
+      }
+      {
+        ProfScope ps(PROF_COMPACT, st);
+        if (nb < tile) XP_CHECK(cudaMemsetAsync(lay.keys + (int64_t)nb * N, 0, sizeof(unsigned long long), st));
+        size_t tmp = lay.cub_bytes;
+        XP_CHECK(cub::DeviceScan::ExclusiveSum(lay.cub_tmp, tmp, lay.keys, lay.scanned, (int64_t)nb * N + 1, st));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        XP_LAUNCH(compact_finalize_kernel, dim3((unsigned)ceil_div(N, 256), (unsigned)nb), 256, 0, st, lay.keys, lay.scanned, N,
+                  lay.act_list, lay.rowptr_c, (kind == XPGNN_CONV_GCN && !l0_rows) ? lay.wgt : nullptr, lay.slot_info, lay.slot_base);
+        XP_LAUNCH(compact_tilemap_kernel, 1, 256, 0, st, lay.slot_info, nb, lay.slot_tile_start, lay.n_tiles, lay.tile_map, NL, stats, lay.counters);
+        XP_LAUNCH(compact_edges_kernel, grid_rows, 256, 0, st, R0.rowptr, R0.col, lay.ebits, act, W, w, b0, nb, N, lay.scanned, lay.ccol);
+      }
+      float* cur = lay.hbuf[0];
+      float* nxt = lay.hbuf[1];
+      for (int l = 0; l < NL; ++l) {
+        const xpgnn_layer_t& L = p->layers_host[l];
+        const xpgnn_relation_t& R = L.rel_host[0];
+        const bool next_gcn = (l + 1 < NL) && kind == XPGNN_CONV_GCN;
+        CspmmArgs s{};
+        s.nb = nb; s.N = N; s.kind = kind; s.layer0 = l == 0;
+        s.slot_info = lay.slot_info; s.slot_tile_start = lay.slot_tile_start; s.act_list = lay.act_list;
+        s.rowptr_c = lay.rowptr_c; s.slot_base = lay.slot_base; s.ccol = lay.ccol;
+        s.in_chunk_stride = cstride; s.out_s_stride = hstride; s.out_chunk_stride = cstride;
+        s.counter = dyn_sched ? lay.counters + l : nullptr;
+        s.l2_stream = l2_stream; s.l2_gather = l2_gather;
+        if (l == 0 && l0_rows) {
+          L0RowsArgs r{};
+          r.rowptr = R.rowptr; r.col = R.col; r.ebits = lay.ebits; r.act = act; r.W = W; r.w = w; r.b0 = b0; r.nb = nb; r.N = N;
+          r.scale = lay.scale; r.z = lay.zc; r.h0 = L.h_out;
+          if (kind == XPGNN_CONV_SAGE_MEAN) { r.r0c = lay.r0c; r.r0_chunk_stride = cstride; }
+          else r.bias = R.b_nbr;
+          r.out = cur; r.out_s_stride = hstride; r.out_chunk_stride = cstride;
+          r.kind = kind; r.act_fn = L.act; r.prescale = next_gcn;
+          ProfScope ps(PROF_SPMM_INVARIANT, st);
+          const int grid = (int)std::min<int64_t>(ceil_div(N, 8), (int64_t)kNumSMs * 2);
+          void (*k0)(const L0RowsArgs) = L.act == XPGNN_ACT_SIGMOID ? l0_rows_kernel<true> : l0_rows_kernel<false>;
+          XP_CHECK(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, kL0SmemBytes));
+          XP_LAUNCH(k0, grid, 256, kL0SmemBytes, st, r);
+        } else if (l == 0) {  // transform-first: gather the coalition-invariant Z
+          s.n_chunks = L.h_out / cw;
+          s.in = lay.zc; s.in_s_stride = 0; s.wgt = kind == XPGNN_CONV_GCN ? lay.wgt : nullptr;
+          if (kind == XPGNN_CONV_SAGE_MEAN) { s.addend = lay.r0c; s.add_chunk_stride = cstride; }
+          else s.bias = R.b_nbr;
+          s.out = cur; s.act_fn = L.act; s.prescale = next_gcn;
+          if (launch_cspmm(s, cw, st)) return 1;
+        } else {       // aggregate-first, then the dense transform of the active rows
+          s.n_chunks = L.h_in / cw;
+          s.in = cur; s.in_s_stride = hstride; s.wgt = nullptr; s.addend = nullptr;
+          s.out = lay.agg; s.act_fn = XPGNN_ACT_NONE; s.prescale = 0;
+          if (launch_cspmm(s, cw, st)) return 1;
+          const bool sage_root = kind == XPGNN_CONV_SAGE_MEAN && R.w_root;
+          DenseArgs d{};
+          d.in = lay.agg; d.in_s_stride = hstride; d.ld_in = cw; d.k = L.h_in; d.cw_in = cw; d.cw_in_lg = cw_lg; d.in_chunk_stride = cstride;
+          d.w = R.w_nbr; d.b = R.b_nbr; d.n_out = L.h_out;
+          d.out = nxt; d.out_s_stride = hstride; d.ld_out = cw; d.cw_out = cw; d.cw_out_lg = cw_lg; d.out_chunk_stride = cstride;
+          d.tile_map = lay.tile_map; d.n_tiles_dev = lay.n_tiles; d.slot_rows = lay.act_list; d.slot_rows_stride = N;
+          d.slot_info = lay.slot_info; d.slot_rowptr = lay.rowptr_c;
+          d.rows_per_s = N; d.M = (int64_t)nb * ceil_div(N, 128) * 128; d.dst_lo = 0; d.dst_hi = N;
+          d.act_fn = sage_root ? XPGNN_ACT_NONE : L.act; d.prescale = next_gcn && !sage_root;
+          if (launch_dense(d, st, dense_prec)) return 1;
+          if (sage_root) {
+            DenseArgs rt = d;
+            rt.in = cur; rt.w = R.w_root; rt.b = nullptr; rt.accumulate = 1; rt.act_fn = L.act; rt.prescale = next_gcn;
+            if (launch_dense(rt, st, dense_prec)) return 1;
+          }
+          std::swap(cur, nxt);
+        }
+      }
+      // ---- head on the query rows ----
+      CHeadArgs h{};
+      int max_dim = L0.h_out;
+      h.n_iso = NL - 1;
+      for (int l = 1; l < NL; ++l) {
+        const xpgnn_layer_t& L = p->layers_host[l];
+        const xpgnn_relation_t& R = L.rel_host[0];
+        xpgnn_dense_t& d = h.iso[l - 1];
+        d.in = L.h_in; d.out = L.h_out; d.act = L.act; d.b = R.b_nbr;
+        d.w = kind == XPGNN_CONV_GCN ? R.w_nbr : R.w_root;  // SAGE: the empty mean contributes nothing
+        max_dim = std::max(max_dim, std::max(L.h_in, L.h_out));
+      }
+      h.kind0 = kind; h.act0 = L0.act; h.h0 = L0.h_out; h.zc = lay.zc; h.z_chunk_stride = cstride; h.z_rowmajor = l0_rows;
+      if (kind == XPGNN_CONV_SAGE_MEAN) h.r0c = lay.r0c; else h.bias0 = R0.b_nbr;
+      h.n_head = p->n_head;
+      for (int i = 0; i < p->n_head; ++i) {
+        h.head[i] = p->head_host[i];
+        max_dim = std::max(max_dim, std::max(p->head_host[i].in, p->head_host[i].out));
+      }
+      h.in = cur; h.in_s_stride = hstride; h.in_chunk_stride = cstride; h.dim0 = p->layers_host[NL - 1].h_out; h.cw = cw; h.cw_lg = cw_lg;
+      h.query = p->query; h.n_query = p->n_query; h.out_col = p->out_col;
+      h.y = y + ((int64_t)(w * 32 + b0) - s0) * p->n_query;
+      h.act = act; h.W = W; h.w = w; h.b0 = b0;
+      {
+        ProfScope ps(PROF_HEAD, st);
+        XP_LAUNCH(compact_head_kernel, nb * p->n_query, 128, sizeof(float) * 2 * max_dim, st, h, max_dim);
+      }
+    }
+  }
+  return 0;
+}
+
+}  // namespace xpgnn

@@ -4,8 +4,16 @@
 
 namespace xpgnn {
 
-// out[m][n] (+)= act(sum_k in[m][k] w[n][k] + b[n]); m enumerates (coalition slot s, row) pairs:
-// optional row list, per-slot strides.
+// out[m][n] (+)= act(sum_k in[m][k] w[n][k] + b[n]) (* row scale); m enumerates (coalition slot s, row) pairs.
+//
+// Two ways of naming the rows:
+//   flat     : m = s * rows_per_s + rr, row = rows ? rows[rr] : row_lo + rr            (legacy tile path)
+//   tile map : 128-row tile t -> (slot, first list position) = tile_map[t]; the slot's row list
+//              slot_rows[slot][..] has slot_nrows[slot] live entries, known only on the device
+//              (active nodes of a coalition: compact path, compact.cu)
+// Two operand layouts: row-major (cw == 0, element k of a row at +k) and chunk-major (cw = 16 | 32:
+// element k at (k / cw) * chunk_stride + k % cw, rows cw floats apart -- the layout the masked SpMM
+// gathers from so that one (coalition, chunk) pass has an L2-resident working set).
 struct DenseArgs {
   const float* in;
   int64_t in_s_stride;
@@ -18,15 +26,67 @@ struct DenseArgs {
   int ld_out;
   const int32_t* rows;
   int rows_per_s, row_lo;  // rows == NULL: row = row_lo + (m % rows_per_s)
-  int64_t M;               // n_slots * rows_per_s
+  int64_t M;               // n_slots * rows_per_s (flat) | worst-case tiles * 128 (tile map)
   int accumulate, act_fn;
   int dst_lo, dst_hi;      // rows outside [dst_lo, dst_hi) are skipped (row lists of hetero layers)
+  // ---- chunk-major operands ----
+  int cw_in, cw_in_lg, cw_out, cw_out_lg;  // 0: row-major
+  int64_t in_chunk_stride, out_chunk_stride;
+  // ---- tile map (device-side row counts) ----
+  const int2* tile_map;        // [*n_tiles_dev] (slot, first position in the slot's row list)
+  const int32_t* n_tiles_dev;
+  const int32_t* slot_rows;    // [slot][slot_rows_stride]
+  int64_t slot_rows_stride;
+  const int2* slot_info;       // [slot] .x = live rows of the list
+  const uint32_t* slot_rowptr; // [slot][slot_rows_stride + 1] compact in-edge offsets (prescale)
+  int prescale;                // 1: multiply the finished row by (1 + masked in-degree)^-1/2 (GCN operand of the next layer)
 };
 
 __device__ __forceinline__ float apply_act(float x, int a) {
   if (a == XPGNN_ACT_RELU) return fmaxf(x, 0.0f);
   if (a == XPGNN_ACT_SIGMOID) return 1.0f / (1.0f + expf(-x));
   return x;
+}
+
+__device__ __forceinline__ float gcn_dinv(uint32_t masked_in_degree) { return 1.0f / sqrtf(1.0f + (float)masked_in_degree); }
+
+struct DenseRow {
+  int64_t io, oo;  // element offsets of the row's first element in `in` / `out`
+  float rs;        // row scale of the epilogue
+};
+
+// row r (0..127) of 128-row tile `tile`; false: the row does not exist / is outside the destination range
+__device__ __forceinline__ bool dense_resolve_row(const DenseArgs& a, int64_t tile, int r, DenseRow& o) {
+  o.rs = 1.0f;
+  if (a.tile_map) {
+    const int2 tm = a.tile_map[tile];
+    const int rr = tm.y + r;
+    if (rr >= a.slot_info[tm.x].x) return false;
+    const int v = a.slot_rows[(int64_t)tm.x * a.slot_rows_stride + rr];
+    o.io = (int64_t)tm.x * a.in_s_stride + (int64_t)v * a.ld_in;
+    o.oo = (int64_t)tm.x * a.out_s_stride + (int64_t)v * a.ld_out;
+    if (a.prescale) {
+      const uint32_t* rp = a.slot_rowptr + (int64_t)tm.x * (a.slot_rows_stride + 1) + rr;
+      o.rs = gcn_dinv(rp[1] - rp[0]);
+    }
+    return true;
+  }
+  const uint32_t m = (uint32_t)tile * 128u + (uint32_t)r;  // M < 2^31 (checked on the host): 32-bit div, not 64-bit
+  if (m >= (uint32_t)a.M) return false;
+  const uint32_t sl = m / (uint32_t)a.rows_per_s;
+  const int rr = (int)(m - sl * (uint32_t)a.rows_per_s);
+  const int v = a.rows ? a.rows[rr] : a.row_lo + rr;
+  if (v < a.dst_lo || v >= a.dst_hi) return false;
+  o.io = (int64_t)sl * a.in_s_stride + (int64_t)v * a.ld_in;
+  o.oo = (int64_t)sl * a.out_s_stride + (int64_t)v * a.ld_out;
+  return true;
+}
+
+__device__ __forceinline__ int64_t dense_in_off(const DenseArgs& a, int kk) {
+  return a.cw_in ? (int64_t)(kk >> a.cw_in_lg) * a.in_chunk_stride + (kk & (a.cw_in - 1)) : (int64_t)kk;
+}
+__device__ __forceinline__ int64_t dense_out_off(const DenseArgs& a, int n) {
+  return a.cw_out ? (int64_t)(n >> a.cw_out_lg) * a.out_chunk_stride + (n & (a.cw_out - 1)) : (int64_t)n;
 }
 
 enum { DENSE_SIMT = 0, DENSE_TC_BF16 = 1, DENSE_TC_TF32X3 = 2 };

@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const DenseArgs
   __shared__ uint64_t bar_acc;
   __shared__ uint32_t tmem_base_sh;
   __shared__ int64_t out_off[TM];
+  __shared__ float row_scale[TM];
   __shared__ __align__(16) float s_bias[256];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const DenseArgs
   const uint32_t idesc = make_idesc(MODE == 0 ? 2 : 1, TM, n_pad);
   const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
   const int n_chunks = K / Cfg::KC;
-  const int64_t n_tiles = (a.M + TM - 1) / TM;
+  const int64_t n_tiles = a.tile_map ? (int64_t)*a.n_tiles_dev : (a.M + TM - 1) / TM;
   uint32_t uses0 = 0u, uses1 = 0u;  // per-stage use counters (scalars: a dynamically indexed array would live in local memory)
   uint32_t chunk_ctr = 0, tile_ctr = 0;
 
@@ -193,19 +194,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const DenseArgs
       const int unit = warp * 4 + it;
       const int r = (unit >> 1) * 8 + lr;
       const int j = (unit & 1) * 4 + lj;
-      const uint32_t m = (uint32_t)tile * TM + r;  // M < 2^31 (checked on the host): 32-bit div, not 64-bit
-      int64_t io = -1;
-      if (m < (uint32_t)a.M) {
-        const uint32_t sl = m / (uint32_t)a.rows_per_s;
-        const int rr = (int)(m - sl * (uint32_t)a.rows_per_s);
-        const int v = a.rows ? a.rows[rr] : a.row_lo + rr;
-        if (v >= a.dst_lo && v < a.dst_hi) io = (int64_t)sl * a.in_s_stride + (int64_t)v * a.ld_in;
-      }
+      DenseRow row;
+      const bool ok = dense_resolve_row(a, tile, r, row);
+      const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
       if (MODE == 0) {
-        buf[it] = io >= 0 ? __ldg(reinterpret_cast<const float4*>(a.in + io + kc * Cfg::KC + j * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        buf[it] = ok ? __ldg(reinterpret_cast<const float4*>(a.in + row.io + dense_in_off(a, kc * Cfg::KC + j * 4))) : zero;
       } else {
-        buf[2 * it] = io >= 0 ? __ldg(reinterpret_cast<const float4*>(a.in + io + kc * Cfg::KC + j * 8)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        buf[2 * it + 1] = io >= 0 ? __ldg(reinterpret_cast<const float4*>(a.in + io + kc * Cfg::KC + j * 8 + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        buf[2 * it] = ok ? __ldg(reinterpret_cast<const float4*>(a.in + row.io + dense_in_off(a, kc * Cfg::KC + j * 8))) : zero;
+        buf[2 * it + 1] = ok ? __ldg(reinterpret_cast<const float4*>(a.in + row.io + dense_in_off(a, kc * Cfg::KC + j * 8 + 4))) : zero;
       }
     }
   };
@@ -226,15 +222,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const DenseArgs
   auto step = [&](float4 (&use)[NV], float4 (&pre)[NV]) -> bool {
     if (tile >= n_tiles) return false;
     if (kc == 0 && tid < TM) {
-      const uint32_t m = (uint32_t)tile * TM + tid;
-      int64_t oo = -1;
-      if (m < (uint32_t)a.M) {
-        const uint32_t s = m / (uint32_t)a.rows_per_s;
-        const int rr = (int)(m - s * (uint32_t)a.rows_per_s);
-        const int v = a.rows ? a.rows[rr] : a.row_lo + rr;
-        if (v >= a.dst_lo && v < a.dst_hi) oo = (int64_t)s * a.out_s_stride + (int64_t)v * a.ld_out;
-      }
-      out_off[tid] = oo;
+      DenseRow row;
+      const bool ok = dense_resolve_row(a, tile, tid, row);
+      out_off[tid] = ok ? row.oo : -1;
+      row_scale[tid] = row.rs;
     }
     {
       const int64_t t2 = item_tile(item + 2);
@@ -308,9 +299,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const DenseArgs
     {
       const int row = (warp & 3) * 32 + lane;          // TMEM lane == tile row; warp w may touch lanes 32*(w%4)..
       const int64_t oo = out_off[row];
+      const float rs = row_scale[row];
       // ReLU and identity share one branch-free path (max with 0 or -inf); sigmoid is a separate loop
       const float lower = a.act_fn == XPGNN_ACT_RELU ? 0.0f : -INFINITY;
-      const bool vec_ok = (a.n_out & 3) == 0 && (a.ld_out & 3) == 0 && (a.out_s_stride & 3) == 0;
+      const bool vec_ok = (a.n_out & 3) == 0 && (a.ld_out & 3) == 0 && (a.out_s_stride & 3) == 0 && (a.out_chunk_stride & 3) == 0;
       for (int c0 = (warp >> 2) * 32; c0 < n_pad; c0 += 64) {
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, r);
@@ -320,7 +312,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const DenseArgs
           if (a.accumulate) {
 #pragma unroll
             for (int c = 0; c < 8; ++c)
-              prev[c] = (c0 + 4 * c < a.n_out) ? *reinterpret_cast<const float4*>(a.out + oo + c0 + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+              prev[c] = (c0 + 4 * c < a.n_out) ? *reinterpret_cast<const float4*>(a.out + oo + dense_out_off(a, c0 + 4 * c))
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
           }
 #pragma unroll
           for (int c = 0; c < 32; c += 4) {
@@ -338,15 +331,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const DenseArgs
             } else {
               v.x = fmaxf(v.x, lower); v.y = fmaxf(v.y, lower); v.z = fmaxf(v.z, lower); v.w = fmaxf(v.w, lower);
             }
-            *reinterpret_cast<float4*>(a.out + oo + n) = v;
+            v.x *= rs; v.y *= rs; v.z *= rs; v.w *= rs;
+            *reinterpret_cast<float4*>(a.out + oo + dense_out_off(a, n)) = v;
           }
         } else {
           for (int c = 0; c < 32; ++c) {
             const int n = c0 + c;
             if (n >= a.n_out) break;
             float x = __uint_as_float(r[c]) + s_bias[n];
-            if (a.accumulate) x += a.out[oo + n];
-            a.out[oo + n] = apply_act(x, a.act_fn);
+            float* op = a.out + oo + dense_out_off(a, n);
+            if (a.accumulate) x += *op;
+            *op = apply_act(x, a.act_fn) * rs;
           }
         }
       }
@@ -372,7 +367,8 @@ static bool tc_eligible(const DenseArgs& d, int mode) {
   const int kc = mode == 0 ? 32 : 64;
   if (d.k <= 0 || d.k % kc != 0 || d.n_out < 8 || d.n_out > 256) return false;
   if (d.M >= (1ll << 31) - 256 || d.rows_per_s <= 0) return false;
-  if (d.ld_in % 4 != 0 || d.in_s_stride % 4 != 0 || ((uintptr_t)d.in & 15) != 0 || ((uintptr_t)d.w & 15) != 0) return false;
+  if (d.ld_in % 4 != 0 || d.in_s_stride % 4 != 0 || d.in_chunk_stride % 4 != 0 || ((uintptr_t)d.in & 15) != 0 || ((uintptr_t)d.w & 15) != 0)
+    return false;
   const int n_pad = (d.n_out + 15) / 16 * 16;
   const size_t smem = (size_t)n_pad * d.k * (mode == 0 ? 8 : 2) + (size_t)TcCfg<0>::STAGES * TM * KC_BYTES * (mode == 0 ? 2 : 1);
   return smem <= 200 * 1024;

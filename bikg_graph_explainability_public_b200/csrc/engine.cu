@@ -23,6 +23,7 @@
 #include "common.cuh"
 #include "dense_args.cuh"
 #include "fused.cuh"
+#include "engine_internal.cuh"
 
 namespace xpgnn {
 
@@ -229,23 +230,17 @@ __global__ void __launch_bounds__(256) dense_rows_kernel(const DenseArgs a) {
   __shared__ float As[DBK][DBM + 4];
   __shared__ float Bs[DBK][DBN + 4];
   __shared__ int64_t in_off[DBM], out_off[DBM];
+  __shared__ float row_scale[DBM];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int64_t m0 = (int64_t)blockIdx.x * DBM;
+  const int64_t tile = blockIdx.x >> 1;  // 128-row tile of the shared row naming (dense_args.cuh); this CTA takes one half
+  if (a.tile_map && tile >= *a.n_tiles_dev) return;
   const int n0 = blockIdx.y * DBN;
   if (tid < DBM) {
-    const int64_t m = m0 + tid;
-    int64_t io = -1, oo = -1;
-    if (m < a.M) {
-      const int64_t s = m / a.rows_per_s;
-      const int rr = (int)(m - s * a.rows_per_s);
-      const int64_t v = a.rows ? a.rows[rr] : a.row_lo + rr;
-      if (v >= a.dst_lo && v < a.dst_hi) {
-        io = s * a.in_s_stride + v * a.ld_in;
-        oo = s * a.out_s_stride + v * a.ld_out;
-      }
-    }
-    in_off[tid] = io;
-    out_off[tid] = oo;
+    DenseRow row;
+    const bool ok = dense_resolve_row(a, tile, (blockIdx.x & 1) * DBM + tid, row);
+    in_off[tid] = ok ? row.io : -1;
+    out_off[tid] = ok ? row.oo : -1;
+    row_scale[tid] = row.rs;
   }
   __syncthreads();
   float acc[4][4];
@@ -259,7 +254,7 @@ __global__ void __launch_bounds__(256) dense_rows_kernel(const DenseArgs a) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int kk = k0 + lk + i;
-      As[lk + i][lr] = (io >= 0 && kk < a.k) ? __ldg(a.in + io + kk) : 0.0f;
+      As[lk + i][lr] = (io >= 0 && kk < a.k) ? __ldg(a.in + io + dense_in_off(a, kk)) : 0.0f;
       const int n = n0 + lr;
       Bs[lk + i][lr] = (n < a.n_out && kk < a.k) ? __ldg(a.w + (int64_t)n * a.k + kk) : 0.0f;
     }
@@ -282,13 +277,15 @@ __global__ void __launch_bounds__(256) dense_rows_kernel(const DenseArgs a) {
   for (int i = 0; i < 4; ++i) {
     const int64_t oo = out_off[ty * 4 + i];
     if (oo < 0) continue;
+    const float rs = row_scale[ty * 4 + i];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tx * 4 + j;
       if (n >= a.n_out) continue;
       float x = acc[i][j] + (a.b ? __ldg(a.b + n) : 0.0f);
-      if (a.accumulate) x += a.out[oo + n];
-      a.out[oo + n] = apply_act(x, a.act_fn);
+      float* op = a.out + oo + dense_out_off(a, n);
+      if (a.accumulate) x += *op;
+      *op = apply_act(x, a.act_fn) * rs;
     }
   }
 }
@@ -350,43 +347,17 @@ __global__ void stats_accum_kernel(const unsigned long long* tile_active, int n_
 }
 
 // ------------------------------------------------------------------------------------------ host side
-// Optional per-category kernel timing with CUDA events on the launching stream (bench.py roofline).
-enum { PROF_SCALE = 0, PROF_SPMM_INVARIANT, PROF_SPMM_TILE, PROF_DENSE, PROF_HEAD, PROF_N };
-struct Profile {
-  bool on = false;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[PROF_N];
-  void reset() {
-    for (auto& v : ev) {
-      for (auto& e : v) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
-      v.clear();
-    }
-  }
-};
-static Profile g_prof;
-struct ProfScope {
-  cudaStream_t st;
-  cudaEvent_t stop = nullptr;
-  ProfScope(int cat, cudaStream_t s) : st(s) {
-    if (!g_prof.on) return;
-    cudaEvent_t a, b;
-    cudaEventCreate(&a);
-    cudaEventCreate(&b);
-    cudaEventRecord(a, st);
-    g_prof.ev[cat].push_back({a, b});
-    stop = b;
-  }
-  ~ProfScope() { if (stop) cudaEventRecord(stop, st); }
-};
+Profile g_prof;
 
 // precision: DENSE_SIMT exact fp32 FMA | DENSE_TC_TF32X3 fp32 via 3 TF32 MMAs | DENSE_TC_BF16
-static int launch_dense(const DenseArgs& d, cudaStream_t st, int precision = DENSE_SIMT) {
+int launch_dense(const DenseArgs& d, cudaStream_t st, int precision) {
   if (d.M <= 0 || d.n_out <= 0) return 0;
   ProfScope ps(PROF_DENSE, st);
   if (precision != DENSE_SIMT && d.M >= 1024) {
     const int mode = precision == DENSE_TC_BF16 ? 1 : 0;
     if (dense_tc_eligible(d, mode)) return launch_dense_tc(d, mode, st);
   }
-  dim3 grid((unsigned)ceil_div(d.M, DBM), (unsigned)ceil_div(d.n_out, DBN));
+  dim3 grid((unsigned)(2 * ceil_div(d.M, 2 * DBM)), (unsigned)ceil_div(d.n_out, DBN));
   XP_LAUNCH(dense_rows_kernel, grid, 256, 0, st, d);
   return 0;
 }
@@ -402,19 +373,6 @@ static int launch_spmm(const SpmmArgs& s, cudaStream_t st) {
   else XP_LAUNCH(spmm_masked_kernel<1>, grid, 256, 0, st, s);
   return 0;
 }
-
-struct Bump {
-  char* base;
-  int64_t off = 0, cap;
-  Bump(void* p, int64_t c) : base((char*)p), cap(c) {}
-  template <class T>
-  T* take(int64_t n) {
-    off = (off + 255) & ~255ll;
-    T* r = base ? reinterpret_cast<T*>(base + off) : nullptr;
-    off += n * (int64_t)sizeof(T);
-    return r;
-  }
-};
 
 struct Layout {
   std::vector<float*> zn;      // layer-0 per-relation transformed sources (biased pointer: index by global id)
@@ -523,6 +481,7 @@ int xpgnn_profile_read(double* ms_host, int64_t* launches_host) {
 
 int64_t xpgnn_forward_workspace_bytes(const xpgnn_plan_t* plan, int32_t tile_coalitions) {
   if (!plan || plan->n_layers < 1 || tile_coalitions < 1 || tile_coalitions > 32) return -1;
+  if (compact_eligible(plan)) return compact_workspace_bytes(plan, tile_coalitions);
   std::vector<UniqueCsr> uniq;
   std::vector<std::vector<int>> map;
   collect_unique(plan, uniq, map);
@@ -541,7 +500,7 @@ int xpgnn_dense_rows(const float* in, int64_t rows, int32_t k, int32_t ld_in, co
     ProfScope ps(PROF_DENSE, (cudaStream_t)stream);
     return launch_dense_tc(d, precision == DENSE_TC_BF16 ? 1 : 0, (cudaStream_t)stream);
   }
-  return launch_dense(d, (cudaStream_t)stream);
+  return launch_dense(d, (cudaStream_t)stream, DENSE_SIMT);
 }
 
 int xpgnn_forward(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32_t s0, int32_t n_s, float* y, void* workspace,
@@ -558,6 +517,7 @@ int xpgnn_forward(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32_t
   XP_REQUIRE(!p->prune || p->hop, "prune = 1 needs the hop levels");
   if (n_s == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  if (compact_eligible(p)) return forward_compact(p, act, W, s0, n_s, y, workspace, workspace_bytes, stats, st, dense_prec);
   const int N = p->n_nodes, NL = p->n_layers;
 
   std::vector<UniqueCsr> uniq;

@@ -192,8 +192,8 @@ int xpgnn_dense_rows(const float* in, int64_t rows, int32_t k, int32_t ld_in, co
 /* Measurement hook (bench.py roofline): when enabled, every engine kernel launch is bracketed by
  * CUDA events on its stream.  xpgnn_profile_read synchronises those events and returns, per
  * category {masked degree, SpMM on the coalition-invariant operand (layer 0), SpMM on coalition-
- * specific activations (layers >= 1), dense transform, head}, the summed device time in ms and the
- * number of launches.  Both arrays are HOST arrays of 5 entries. */
+ * specific activations (layers >= 1), dense transform, head, per-tile compaction of the active edge lists},
+ * the summed device time in ms and the number of launches.  Both arrays are HOST arrays of 6 entries. */
 int xpgnn_profile(int32_t enable);
 int xpgnn_profile_read(double* ms_host, int64_t* launches_host);
 

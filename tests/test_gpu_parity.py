@@ -253,6 +253,7 @@ def test_fused_spmm_dense_matches_oracle(hidden, lib, monkeypatch):
     act = torch.zeros((n, w), dtype=torch.int32, device="cuda")
     _lib.check(lib.xpgnn_pack_mask(m8.data_ptr(), s, n, act.data_ptr(), w, None, _lib.stream_ptr()))
     ys = {}
+    monkeypatch.setenv("XPGNN_COMPACT", "0")  # the compact path would take these shapes first
     for fused in ("1", "0"):
         monkeypatch.setenv("XPGNN_FUSED", fused)
         eng = MaskedForward(GraphSpec(x.cuda(), ei.cuda(), [0, n]), lower(arch), [q])
@@ -264,6 +265,62 @@ def test_fused_spmm_dense_matches_oracle(hidden, lib, monkeypatch):
     monkeypatch.setenv("XPGNN_FUSED_SB", "8")
     eng = MaskedForward(GraphSpec(x.cuda(), ei.cuda(), [0, n]), lower(arch), [q], tile_coalitions=8)
     np.testing.assert_allclose(eng(act, s)[:, 0].cpu().numpy(), ys["1"], rtol=2e-5, atol=1e-6)
+
+
+def _pack(lib, mask):
+    from bikg_graph_explainability_public_b200 import _lib
+
+    s, n = mask.shape
+    m8 = mask.to(torch.uint8).cuda().contiguous()
+    w = -(-s // 32)
+    act = torch.zeros((n, w), dtype=torch.int32, device="cuda")
+    _lib.check(lib.xpgnn_pack_mask(m8.data_ptr(), s, n, act.data_ptr(), w, None, _lib.stream_ptr()))
+    return act
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,hidden,env", [
+    ("gcn", (128, 128), {}),                          # row-outer layer 0 + list-driven layer 1 (the C3 shape)
+    ("gcn", (128, 128), {"XPGNN_L0": "lists"}),       # list-driven layer 0 with per-source weights
+    ("gcn", (128, 128), {"XPGNN_SCHED": "static"}),
+    ("sage", (128, 128), {}),
+    ("sage", (128, 128), {"XPGNN_L0": "lists"}),
+    ("gcn", (128,), {}),                              # single conv layer
+    ("gcn", (16,), {}),                               # 16-wide chunks, SIMT transforms
+    ("gcn", (32, 48), {}),
+    ("sage", (64, 128, 64), {}),
+    ("gcn", (192, 128), {}),                          # three 64-column blocks in the row-outer kernel
+])
+def test_compact_path_matches_oracle(kind, hidden, env, lib, monkeypatch):
+    """Compact path (compact.cu: active rows only, per-coalition compacted edge lists, chunk-major
+    activations) vs the oracle and vs the tile path of engine.cu, incl. coalitions in which the query
+    node is inactive (isolated chain in the head), a partial last word and memory-limited tiles."""
+    from bikg_graph_explainability_public_b200.engine import GraphSpec, MaskedForward
+    from bikg_graph_explainability_public_b200.lowering import lower
+    from oracle.xpgnn_oracle import kernel_output
+
+    x, ei, arch, mask, q = _random_model_case(7, kind, n=900, e=9000, f=40, hidden=hidden, s=75)
+    s, n = mask.shape
+    _, y_ref = kernel_output(mask.numpy(), x, ei.numpy(), arch, q)
+    y_ref = y_ref.numpy().reshape(-1)
+    assert (~mask[:, q]).sum() > 5 and mask[:, q].sum() > 5   # both the active and the isolated query branch
+    act = _pack(lib, mask)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    g = GraphSpec(x.cuda(), ei.cuda(), [0, n])
+    eng = MaskedForward(g, lower(arch), [q, (q + 1) % n, 5])
+    y = eng(act, s).cpu().numpy()
+    np.testing.assert_allclose(y[:, 0], y_ref, rtol=Y_RTOL, atol=Y_ATOL)
+    _, y_ref2 = kernel_output(mask.numpy(), x, ei.numpy(), arch, 5)
+    np.testing.assert_allclose(y[:, 2], y_ref2.numpy().reshape(-1), rtol=Y_RTOL, atol=Y_ATOL)
+    # sub-range (a rank's shard) and a memory-limited tile
+    np.testing.assert_array_equal(eng(act, s, 32, 43).cpu().numpy(), y[32:75])
+    eng8 = MaskedForward(g, lower(arch), [q, (q + 1) % n, 5], tile_coalitions=8)
+    np.testing.assert_allclose(eng8(act, s).cpu().numpy(), y, rtol=1e-6, atol=1e-7)
+    # the tile path of engine.cu computes every row; same predictions
+    monkeypatch.setenv("XPGNN_COMPACT", "0")
+    legacy = MaskedForward(g, lower(arch), [q, (q + 1) % n, 5])
+    np.testing.assert_allclose(legacy(act, s).cpu().numpy(), y, rtol=2e-5, atol=1e-6)
 
 
 @pytest.mark.parametrize("kind", ["gcn", "sage"])
