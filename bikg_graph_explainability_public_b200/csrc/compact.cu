@@ -68,9 +68,19 @@ __global__ void __launch_bounds__(256) compact_finalize_kernel(const unsigned lo
                                                                const unsigned long long* __restrict__ scanned, int N,
                                                                int32_t* __restrict__ act_list, uint32_t* __restrict__ rowptr_c,
                                                                float* __restrict__ wgt, int2* __restrict__ slot_info,
-                                                               long long* __restrict__ slot_base) {
+                                                               long long* __restrict__ slot_base, int32_t* __restrict__ rows_packed,
+                                                               float* __restrict__ rs_packed) {
   const int t = blockIdx.y;
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  // first 128-row tile of this slot in the concatenated, per-slot padded tile table
+  __shared__ int s_tile0;
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int q = 0; q < t; ++q)
+      acc += ((int)((scanned[(int64_t)(q + 1) * N] >> kKeyShift) - (scanned[(int64_t)q * N] >> kKeyShift)) + 127) / 128;
+    s_tile0 = acc;
+  }
+  __syncthreads();
   if (v >= N) return;
   const int64_t g = (int64_t)t * N + v;
   const unsigned long long K = keys[g], S = scanned[g], B = scanned[(int64_t)t * N];
@@ -78,6 +88,8 @@ __global__ void __launch_bounds__(256) compact_finalize_kernel(const unsigned lo
     const int64_t i = (int64_t)((S >> kKeyShift) - (B >> kKeyShift));
     act_list[(int64_t)t * N + i] = v;
     rowptr_c[(int64_t)t * (N + 1) + i] = (uint32_t)((S & kEdgeMask) - (B & kEdgeMask));
+    rows_packed[(int64_t)s_tile0 * 128 + i] = (int32_t)(((uint32_t)t << kPackShift) | (uint32_t)v);
+    rs_packed[(int64_t)s_tile0 * 128 + i] = gcn_dinv((uint32_t)(K & kEdgeMask));
   }
   if (wgt) wgt[g] = gcn_dinv((uint32_t)(K & kEdgeMask));
   if (v == N - 1) {
@@ -87,12 +99,13 @@ __global__ void __launch_bounds__(256) compact_finalize_kernel(const unsigned lo
     rowptr_c[(int64_t)t * (N + 1) + n_act] = (uint32_t)tot;
     slot_info[t] = make_int2(n_act, (int)min(tot, (unsigned long long)INT_MAX));
     slot_base[t] = (long long)(B & kEdgeMask);
+    for (int i = n_act; i < (n_act + 127) / 128 * 128; ++i) rows_packed[(int64_t)s_tile0 * 128 + i] = -1;  // pad the last tile
   }
 }
 
-// 128-row tiles of every slot's active-row list (the dense transform's work list) + stats
+// first 128-row tile of every slot's active-row list, tile total, work counters, stats
 __global__ void __launch_bounds__(256) compact_tilemap_kernel(const int2* __restrict__ slot_info, int nb, int32_t* __restrict__ slot_tile_start,
-                                                              int32_t* __restrict__ n_tiles, int2* __restrict__ tile_map, int n_layers,
+                                                              int32_t* __restrict__ n_tiles, int n_layers,
                                                               int64_t* stats, int32_t* __restrict__ counters) {
   __shared__ int start[33];
   if (threadIdx.x < 16) counters[threadIdx.x] = 0;  // work counters of the SpMM launches of this tile
@@ -113,8 +126,6 @@ __global__ void __launch_bounds__(256) compact_tilemap_kernel(const int2* __rest
   }
   __syncthreads();
   if (threadIdx.x <= nb) slot_tile_start[threadIdx.x] = start[threadIdx.x];
-  for (int t = 0; t < nb; ++t)
-    for (int k = threadIdx.x; k < start[t + 1] - start[t]; k += blockDim.x) tile_map[start[t] + k] = make_int2(t, k * 128);
 }
 
 // pass 3: per-coalition compacted source lists (original node ids, CSR order kept)
@@ -524,7 +535,7 @@ static int compact_cw(const xpgnn_plan_t* p) {
 
 bool compact_eligible(const xpgnn_plan_t* p) {
   if (!compact_enabled() || p->prune || p->zero_edge_rule || p->n_layers < 1 || p->n_layers > std::min(kMaxConvIso, 16)) return false;
-  if (p->n_head > kMaxHeadC) return false;
+  if (p->n_head > kMaxHeadC || p->n_nodes >= (1 << kPackShift)) return false;
   const xpgnn_relation_t& R0 = p->layers_host[0].rel_host[0];
   for (int l = 0; l < p->n_layers; ++l) {
     const xpgnn_layer_t& L = p->layers_host[l];
@@ -550,7 +561,8 @@ struct CLayout {
   int2* slot_info;
   long long* slot_base;
   int32_t *slot_tile_start, *n_tiles, *counters;
-  int2* tile_map;
+  int32_t* rows_packed;
+  float* rs_packed;
   int32_t* ccol;
   float *hbuf[2], *agg;
   int64_t bytes;
@@ -581,7 +593,8 @@ static CLayout compact_carve(const xpgnn_plan_t* p, void* ws, int64_t cap, int t
   c.slot_tile_start = b.take<int32_t>(33);
   c.n_tiles = b.take<int32_t>(1);
   c.counters = b.take<int32_t>(16);
-  c.tile_map = b.take<int2>((int64_t)tile * ceil_div(N, 128));
+  c.rows_packed = b.take<int32_t>((int64_t)tile * ceil_div(N, 128) * 128);
+  c.rs_packed = b.take<float>((int64_t)tile * ceil_div(N, 128) * 128);
   c.ccol = b.take<int32_t>((int64_t)tile * E);
   c.hbuf[0] = b.take<float>((int64_t)tile * N * hmax);
   if (NL > 1) {
@@ -672,8 +685,9 @@ int forward_compact(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32
         XP_CHECK(cub::DeviceScan::ExclusiveSum(lay.cub_tmp, tmp, lay.keys, lay.scanned, (int64_t)nb * N + 1, st));
         g_launches.fetch_add(1, std::memory_order_relaxed);
         XP_LAUNCH(compact_finalize_kernel, dim3((unsigned)ceil_div(N, 256), (unsigned)nb), 256, 0, st, lay.keys, lay.scanned, N,
-                  lay.act_list, lay.rowptr_c, (kind == XPGNN_CONV_GCN && !l0_rows) ? lay.wgt : nullptr, lay.slot_info, lay.slot_base);
-        XP_LAUNCH(compact_tilemap_kernel, 1, 256, 0, st, lay.slot_info, nb, lay.slot_tile_start, lay.n_tiles, lay.tile_map, NL, stats, lay.counters);
+                  lay.act_list, lay.rowptr_c, (kind == XPGNN_CONV_GCN && !l0_rows) ? lay.wgt : nullptr, lay.slot_info, lay.slot_base,
+                  lay.rows_packed, lay.rs_packed);
+        XP_LAUNCH(compact_tilemap_kernel, 1, 256, 0, st, lay.slot_info, nb, lay.slot_tile_start, lay.n_tiles, NL, stats, lay.counters);
         XP_LAUNCH(compact_edges_kernel, grid_rows, 256, 0, st, R0.rowptr, R0.col, lay.ebits, act, W, w, b0, nb, N, lay.scanned, lay.ccol);
       }
       float* cur = lay.hbuf[0];
@@ -719,14 +733,13 @@ int forward_compact(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32
           d.in = lay.agg; d.in_s_stride = hstride; d.ld_in = cw; d.k = L.h_in; d.cw_in = cw; d.cw_in_lg = cw_lg; d.in_chunk_stride = cstride;
           d.w = R.w_nbr; d.b = R.b_nbr; d.n_out = L.h_out;
           d.out = nxt; d.out_s_stride = hstride; d.ld_out = cw; d.cw_out = cw; d.cw_out_lg = cw_lg; d.out_chunk_stride = cstride;
-          d.tile_map = lay.tile_map; d.n_tiles_dev = lay.n_tiles; d.slot_rows = lay.act_list; d.slot_rows_stride = N;
-          d.slot_info = lay.slot_info; d.slot_rowptr = lay.rowptr_c;
+          d.rows_packed = lay.rows_packed; d.n_tiles_dev = lay.n_tiles;
           d.rows_per_s = N; d.M = (int64_t)nb * ceil_div(N, 128) * 128; d.dst_lo = 0; d.dst_hi = N;
-          d.act_fn = sage_root ? XPGNN_ACT_NONE : L.act; d.prescale = next_gcn && !sage_root;
+          d.act_fn = sage_root ? XPGNN_ACT_NONE : L.act; d.rs_packed = (next_gcn && !sage_root) ? lay.rs_packed : nullptr;
           if (launch_dense(d, st, dense_prec)) return 1;
           if (sage_root) {
             DenseArgs rt = d;
-            rt.in = cur; rt.w = R.w_root; rt.b = nullptr; rt.accumulate = 1; rt.act_fn = L.act; rt.prescale = next_gcn;
+            rt.in = cur; rt.w = R.w_root; rt.b = nullptr; rt.accumulate = 1; rt.act_fn = L.act; rt.rs_packed = next_gcn ? lay.rs_packed : nullptr;
             if (launch_dense(rt, st, dense_prec)) return 1;
           }
           std::swap(cur, nxt);

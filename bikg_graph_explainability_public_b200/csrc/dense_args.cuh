@@ -32,15 +32,12 @@ struct DenseArgs {
   // ---- chunk-major operands ----
   int cw_in, cw_in_lg, cw_out, cw_out_lg;  // 0: row-major
   int64_t in_chunk_stride, out_chunk_stride;
-  // ---- tile map (device-side row counts) ----
-  const int2* tile_map;        // [*n_tiles_dev] (slot, first position in the slot's row list)
+  // ---- tile table (device-side row counts): entry [tile * 128 + r] = slot << 26 | node id, or -1 ----
+  const int32_t* rows_packed;
   const int32_t* n_tiles_dev;
-  const int32_t* slot_rows;    // [slot][slot_rows_stride]
-  int64_t slot_rows_stride;
-  const int2* slot_info;       // [slot] .x = live rows of the list
-  const uint32_t* slot_rowptr; // [slot][slot_rows_stride + 1] compact in-edge offsets (prescale)
-  int prescale;                // 1: multiply the finished row by (1 + masked in-degree)^-1/2 (GCN operand of the next layer)
+  const float* rs_packed;      // optional row scale per entry: (1 + masked in-degree)^-1/2 (GCN operand of the next layer)
 };
+constexpr int kPackShift = 26;  // node ids < 2^26 in the packed tile table
 
 __device__ __forceinline__ float apply_act(float x, int a) {
   if (a == XPGNN_ACT_RELU) return fmaxf(x, 0.0f);
@@ -58,17 +55,14 @@ struct DenseRow {
 // row r (0..127) of 128-row tile `tile`; false: the row does not exist / is outside the destination range
 __device__ __forceinline__ bool dense_resolve_row(const DenseArgs& a, int64_t tile, int r, DenseRow& o) {
   o.rs = 1.0f;
-  if (a.tile_map) {
-    const int2 tm = a.tile_map[tile];
-    const int rr = tm.y + r;
-    if (rr >= a.slot_info[tm.x].x) return false;
-    const int v = a.slot_rows[(int64_t)tm.x * a.slot_rows_stride + rr];
-    o.io = (int64_t)tm.x * a.in_s_stride + (int64_t)v * a.ld_in;
-    o.oo = (int64_t)tm.x * a.out_s_stride + (int64_t)v * a.ld_out;
-    if (a.prescale) {
-      const uint32_t* rp = a.slot_rowptr + (int64_t)tm.x * (a.slot_rows_stride + 1) + rr;
-      o.rs = gcn_dinv(rp[1] - rp[0]);
-    }
+  if (a.rows_packed) {
+    const int64_t pos = tile * 128 + r;
+    const int32_t e = a.rows_packed[pos];
+    if (e < 0) return false;
+    const int64_t slot = (uint32_t)e >> kPackShift, v = e & ((1 << kPackShift) - 1);
+    o.io = slot * a.in_s_stride + v * a.ld_in;
+    o.oo = slot * a.out_s_stride + v * a.ld_out;
+    if (a.rs_packed) o.rs = a.rs_packed[pos];
     return true;
   }
   const uint32_t m = (uint32_t)tile * 128u + (uint32_t)r;  // M < 2^31 (checked on the host): 32-bit div, not 64-bit

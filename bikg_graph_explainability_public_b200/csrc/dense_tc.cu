@@ -14,6 +14,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "dense_args.cuh"
@@ -26,6 +27,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+template <bool BACKOFF = true>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
@@ -37,6 +39,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(done)
         : "r"(addr), "r"(parity)
         : "memory");
+    // waiting warps must not eat the issue slots / shared-memory pipe of the working ones
+    if (BACKOFF && !done) __nanosleep(spin < 4 ? 20 : 100);
     if (spin > (1u << 24)) __trap();  // never hang the GPU: a lost arrival becomes an error
   }
 }
@@ -84,6 +88,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // shared-memory matrix descriptor, no swizzle, K-major: core matrix = 8 rows x 16 B stored contiguously
 // (128 B); LBO = byte stride between core matrices adjacent in K, SBO = between 8-row groups.
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -100,10 +115,15 @@ __host__ __device__ constexpr uint32_t make_idesc(int kind_fmt /*1 bf16, 2 tf32*
 
 // ------------------------------------------------------------------ kernel
 constexpr int TM = 128;          // rows per tile == UMMA M == TMEM lanes
-constexpr int LOADER_WARPS = 8;
-constexpr int TC_THREADS = 32 * (4 + LOADER_WARPS + 1);  // warps 0-3 epilogue, 4-11 loaders / converters, 12 MMA issue
+constexpr int EPI_WARPS = 8;      // two per TMEM lane quarter, each takes every other 16-column block
+constexpr int LOADER_GROUPS = 3;  // chunks in flight per SM
+constexpr int GROUP_WARPS = 4;
+constexpr int LOADER_WARPS = GROUP_WARPS * LOADER_GROUPS;
+constexpr int TC_THREADS = 32 * (EPI_WARPS + LOADER_WARPS + 1);  // warps 0-7 epilogue, 8-19 loaders / converters, 20 MMA issue
+constexpr int MAX_DONE = 12;      // lcm(stages <= 4, LOADER_GROUPS)
 constexpr int KC = 32;           // K elements per stage
 constexpr int MAX_STAGES = 4;
+constexpr int TR_STRIDE = 20;     // floats per row of a 32 x 16 transposition block (16-byte aligned, conflict-free writes)
 
 // MODE 0: TF32x3 (element 4 B, hi/lo copies)   MODE 1: BF16 (element 2 B)
 template <int MODE>
@@ -116,6 +136,15 @@ struct TcCfg {
   static constexpr int A_STAGE_BYTES = PART_BYTES * PARTS;
 };
 
+__device__ __forceinline__ void mbar_wait_timed(uint64_t* bar, uint32_t parity, unsigned long long* dbg, unsigned long long& acc) {
+  if (dbg) {
+    const long long t0 = clock64();
+    mbar_wait<true>(bar, parity);
+    acc += (unsigned long long)(clock64() - t0);
+  } else {
+    mbar_wait<true>(bar, parity);
+  }
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -138,27 +167,35 @@ __device__ __forceinline__ uint2 pack_bf16(const float4& v) {
   return r;
 }
 
-// out of line on purpose (rare paths; the hot epilogue must stay small)
-__device__ __noinline__ void sigmoid4(float4& v) {
+// out of line on purpose (rare paths; the hot epilogue must stay small).  By value / through shared memory:
+// a reference parameter would force the caller's registers into local memory.
+__device__ __noinline__ float4 sigmoid4(float4 v) {
   v.x = apply_act(v.x, XPGNN_ACT_SIGMOID); v.y = apply_act(v.y, XPGNN_ACT_SIGMOID);
   v.z = apply_act(v.z, XPGNN_ACT_SIGMOID); v.w = apply_act(v.w, XPGNN_ACT_SIGMOID);
+  return v;
 }
-__device__ __noinline__ void scalar_epilogue(const DenseArgs& a, const uint32_t (&r)[32], int c0, int64_t oo, float rs, const float* s_bias) {
+// row-per-thread fallback for outputs that cannot be written as float4: `row16` = the thread's 16 accumulators in shared memory
+__device__ __noinline__ void scalar_epilogue(const float* row16, int c0, int n_out, const float* s_bias, float* out_row, int cw_out, int cw_out_lg,
+                                             int64_t out_chunk_stride, int accumulate, int act_fn, float rs) {
 #pragma unroll 1
-  for (int c = 0; c < 32; ++c) {
+  for (int c = 0; c < 16; ++c) {
     const int n = c0 + c;
-    if (n >= a.n_out) break;
-    float x = __uint_as_float(r[c]) + s_bias[n];
-    float* op = a.out + oo + dense_out_off(a, n);
-    if (a.accumulate) x += *op;
-    *op = apply_act(x, a.act_fn) * rs;
+    if (n >= n_out) break;
+    float x = row16[c] + s_bias[n];
+    float* op = out_row + (cw_out ? (int64_t)(n >> cw_out_lg) * out_chunk_stride + (n & (cw_out - 1)) : (int64_t)n);
+    if (accumulate) x += *op;
+    *op = apply_act(x, act_fn) * rs;
   }
 }
 
 // out of line on purpose: called once per (tile, row) by the loaders, keeps their unrolled pipeline small
-__device__ __noinline__ const float* resolve_in_row(const DenseArgs& a, int64_t tile, int r) {
+__device__ __noinline__ const float* resolve_in_row(const float* in, int64_t in_s_stride, int ld_in, const int32_t* rows, int rows_per_s,
+                                                   int row_lo, int64_t M, int dst_lo, int dst_hi, int64_t tile, int r) {
+  DenseArgs a{};  // flat row naming only (the tile table is read inline by the loaders)
+  a.in_s_stride = in_s_stride; a.ld_in = ld_in; a.rows = rows; a.rows_per_s = rows_per_s; a.row_lo = row_lo; a.M = M;
+  a.dst_lo = dst_lo; a.dst_hi = dst_hi;
   DenseRow row;
-  return dense_resolve_row(a, tile, r, row) ? a.in + row.io : nullptr;
+  return dense_resolve_row(a, tile, r, row) ? in + row.io : nullptr;
 }
 
 // Warp-specialised persistent kernel, one CTA per SM, tiles dealt round-robin:
@@ -169,13 +206,17 @@ __device__ __noinline__ const float* resolve_in_row(const DenseArgs& a, int64_t 
 //   epilogue (4 warps): waits "accumulator full", tcgen05.ld, bias / accumulate / activation / row scale,
 //                       stores, then "accumulator empty".  It overlaps the next tile's loads and MMAs.
 template <int MODE>
-__global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const DenseArgs a, int n_pad, uint32_t tmem_cols, int n_stages) {
+__global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const DenseArgs a, int n_pad, uint32_t tmem_cols, int n_stages, unsigned long long* dbg) {
   using Cfg = TcCfg<MODE>;
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t bar_full[MAX_STAGES], bar_empty[MAX_STAGES];
+  __shared__ uint64_t bar_full[MAX_STAGES];
+  // MMAs of item i done -> bar_done[i % n_done], n_done = lcm(n_stages, LOADER_GROUPS): every barrier is then waited on by
+  // exactly one loader group and in every one of its phases (a parity wait must not skip a phase)
+  __shared__ uint64_t bar_done[MAX_DONE];
   __shared__ uint64_t bar_acc_full[2], bar_acc_empty[2];
   __shared__ uint32_t tmem_base_sh;
   __shared__ __align__(16) float s_bias[256];
+  __shared__ __align__(16) float s_tr[EPI_WARPS * 32 * TR_STRIDE];  // epilogue transposition blocks, one per epilogue warp
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int K = a.k;                                  // multiple of KC
@@ -187,13 +228,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const DenseArgs
   if (warp == 0) tmem_alloc(&tmem_base_sh, tmem_cols);
   if (tid < 256) s_bias[tid] = (a.b && tid < a.n_out) ? a.b[tid] : 0.0f;
   if (tid == 0) {
-    for (int s = 0; s < MAX_STAGES; ++s) {
-      mbar_init(&bar_full[s], 32 * LOADER_WARPS);
-      mbar_init(&bar_empty[s], 1);
-    }
+    for (int s = 0; s < MAX_STAGES; ++s) mbar_init(&bar_full[s], 32 * GROUP_WARPS);
+    for (int s = 0; s < MAX_DONE; ++s) mbar_init(&bar_done[s], 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bar_acc_full[s], 1);
-      mbar_init(&bar_acc_empty[s], 128);
+      mbar_init(&bar_acc_empty[s], 32 * EPI_WARPS);
     }
     fence_mbar_init();
   }
@@ -225,46 +264,70 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const DenseArgs
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_sh;
   const int n_chunks = K / KC;
-  const int64_t n_tiles = a.tile_map ? (int64_t)*a.n_tiles_dev : (a.M + TM - 1) / TM;
+  const int n_done = n_stages % LOADER_GROUPS == 0 ? n_stages : n_stages * LOADER_GROUPS;
+  const int64_t n_tiles = a.rows_packed ? (int64_t)*a.n_tiles_dev : (a.M + TM - 1) / TM;
   const int64_t my_tiles = (int64_t)blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-  if (warp >= 4 && warp < 4 + LOADER_WARPS) {
+  if (warp >= EPI_WARPS && warp < EPI_WARPS + LOADER_WARPS) {
     // ================= loaders / converters =================
-    // a warp owns 16 rows of the tile; per K chunk a thread moves 4 float4 (2 rows x 2 sixteen-byte columns)
-    const int lw = warp - 4, lr = lane & 7, lj = lane >> 3;
+    // LOADER_GROUPS groups of 4 warps take the K chunks round-robin.  A thread has only its own chunk in flight
+    // when it executes fence.proxy.async (the fence waits for every outstanding load of the thread: prefetching
+    // further chunks in the same thread would serialise on it); the depth comes from the groups.
+    // Inside a group a warp owns 32 rows of the tile; per chunk a thread moves 8 float4 (4 rows x 2 columns).
+    const int grp = (warp - EPI_WARPS) / GROUP_WARPS, lw = (warp - EPI_WARPS) % GROUP_WARPS, lr = lane & 7, lj = lane >> 3;
     const int64_t n_items = my_tiles * n_chunks;
     // MODE 0: 16-byte columns lj and lj + 4; MODE 1: the adjacent pair 2 lj, 2 lj + 1 (one bf16 column)
     const int j0 = MODE == 0 ? lj : 2 * lj, j1 = MODE == 0 ? lj + 4 : 2 * lj + 1;
-    // ---- load cursor: rows are resolved once per tile, when its first chunk is requested ----
-    int64_t ld_tile = (int64_t)blockIdx.x - gridDim.x;
-    int ld_kc = n_chunks - 1;
-    const float* ld_row[2] = {nullptr, nullptr};
-    auto load_next = [&](float4 (&buf)[4]) {
-      if (++ld_kc == n_chunks) {
-        ld_kc = 0;
-        ld_tile += gridDim.x;
+    unsigned long long w_empty = 0;
+    const long long t_role0 = clock64();
+    // cursor of this group: item i = (local tile ti, chunk kc), stage st; dn / dn_use = barrier and phase of item i - n_stages
+    int64_t ti = 0;
+    int kc = grp, st = grp % n_stages;
+    while (kc >= n_chunks) { kc -= n_chunks; ++ti; }
+    int64_t cur_ti = -1;
+    const float* ld_row[4] = {nullptr, nullptr, nullptr, nullptr};
+    int32_t nxt_e[4] = {-1, -1, -1, -1};  // tile-table entries of the next tile of this CTA, loaded a tile ahead
+    int64_t nxt_ti = -1;
+    for (int64_t i = grp; i < n_items; i += LOADER_GROUPS) {
+      if (ti != cur_ti) {  // rows of a new tile
+        const int64_t tile = (int64_t)blockIdx.x + ti * gridDim.x;
 #pragma unroll
-        for (int p = 0; p < 2; ++p) {
-          ld_row[p] = resolve_in_row(a, ld_tile, lw * 16 + p * 8 + lr);
+        for (int p = 0; p < 4; ++p) {
+          const int r = lw * 32 + p * 8 + lr;
+          if (a.rows_packed) {
+            const int32_t e = nxt_ti == ti ? nxt_e[p] : __ldg(a.rows_packed + tile * 128 + r);
+            ld_row[p] = e < 0 ? nullptr
+                              : a.in + (int64_t)((uint32_t)e >> kPackShift) * a.in_s_stride + (int64_t)(e & ((1 << kPackShift) - 1)) * a.ld_in;
+          } else {
+            ld_row[p] = resolve_in_row(a.in, a.in_s_stride, a.ld_in, a.rows, a.rows_per_s, a.row_lo, a.M, a.dst_lo, a.dst_hi, tile, r);
+          }
+        }
+        cur_ti = ti;
+      }
+      float4 buf[8];
+      {
+        const int64_t o0 = dense_in_off(a, kc * KC + j0 * 4), o1 = dense_in_off(a, kc * KC + j1 * 4);
+        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          buf[2 * p] = ld_row[p] ? __ldg(reinterpret_cast<const float4*>(ld_row[p] + o0)) : zero;
+          buf[2 * p + 1] = ld_row[p] ? __ldg(reinterpret_cast<const float4*>(ld_row[p] + o1)) : zero;
         }
       }
-      const int64_t o0 = dense_in_off(a, ld_kc * KC + j0 * 4), o1 = dense_in_off(a, ld_kc * KC + j1 * 4);
-      const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a.rows_packed && nxt_ti != ti + 1 && ti + 1 < my_tiles) {  // table entries of the next tile, in flight with the data
+        nxt_ti = ti + 1;
 #pragma unroll
-      for (int p = 0; p < 2; ++p) {
-        buf[2 * p] = ld_row[p] ? __ldg(reinterpret_cast<const float4*>(ld_row[p] + o0)) : zero;
-        buf[2 * p + 1] = ld_row[p] ? __ldg(reinterpret_cast<const float4*>(ld_row[p] + o1)) : zero;
+        for (int p = 0; p < 4; ++p)
+          nxt_e[p] = __ldg(a.rows_packed + ((int64_t)blockIdx.x + nxt_ti * gridDim.x) * 128 + lw * 32 + p * 8 + lr);
       }
-    };
-    // ---- stage cursor ----
-    int st = 0;
-    uint32_t st_use = 0;  // completed rounds over the stage ring
-    auto stage_next = [&](const float4 (&buf)[4]) {
-      if (st_use > 0) mbar_wait(&bar_empty[st], (st_use - 1) & 1u);  // the MMAs that read this stage are done
+      if (i >= n_stages) {  // the MMAs that read this stage (item i - n_stages) are done
+        const int64_t prev = i - n_stages;
+        mbar_wait_timed(&bar_done[prev % n_done], (uint32_t)(prev / n_done) & 1u, dbg, w_empty);
+      }
       uint8_t* stage = sA + (size_t)st * Cfg::A_STAGE_BYTES;
 #pragma unroll
-      for (int p = 0; p < 2; ++p) {
-        const int r = lw * 16 + p * 8 + lr;
+      for (int p = 0; p < 4; ++p) {
+        const int r = lw * 32 + p * 8 + lr;
         if (MODE == 0) {
           float4 hi, lo;
           split_tf32(buf[2 * p], hi, lo);
@@ -280,44 +343,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const DenseArgs
       }
       fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
       mbar_arrive(&bar_full[st]);
-      if (++st == n_stages) {
-        st = 0;
-        ++st_use;
-      }
-    };
-    // three chunks in flight ahead of the one being staged; the four register buffers rotate by unrolling
-    // (the bodies are kept small -- the row lookup is a call -- so that the kernel stays inside the instruction cache)
-    float4 b0[4], b1[4], b2[4], b3[4];
-    int64_t loaded = 0, staged = 0;
-    auto step = [&](float4 (&pre)[4], const float4 (&use)[4]) {
-      if (loaded < n_items) { load_next(pre); ++loaded; }
-      if (staged < n_items) { stage_next(use); ++staged; }
-    };
-    if (loaded < n_items) { load_next(b0); ++loaded; }
-    if (loaded < n_items) { load_next(b1); ++loaded; }
-    if (loaded < n_items) { load_next(b2); ++loaded; }
-    while (staged < n_items) {
-      step(b3, b0);
-      step(b0, b1);
-      step(b1, b2);
-      step(b2, b3);
+      // advance the cursor by LOADER_GROUPS items
+      kc += LOADER_GROUPS;
+      while (kc >= n_chunks) { kc -= n_chunks; ++ti; }
+      st = (st + LOADER_GROUPS) % n_stages;
     }
-  } else if (warp == 4 + LOADER_WARPS) {
+    if (dbg && blockIdx.x == 0 && tid == EPI_WARPS * 32) {
+      dbg[0] = (unsigned long long)(clock64() - t_role0);
+      dbg[1] = w_empty;
+    }
+  } else if (warp == EPI_WARPS + LOADER_WARPS) {
     // ================= MMA issue (one lane) =================
     if (lane == 0) {
       const uint32_t idesc = make_idesc(MODE == 0 ? 2 : 1, TM, n_pad);
       const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
       int64_t item = 0;
+      unsigned long long w_full = 0, w_acc = 0;
+      const long long t_role0 = clock64();
       for (int64_t ti = 0; ti < my_tiles; ++ti) {
         const int ab = (int)(ti & 1);
         if (ti >= 2) {  // the epilogue has drained this accumulator buffer
-          mbar_wait(&bar_acc_empty[ab], (uint32_t)((ti >> 1) - 1) & 1u);
+          mbar_wait_timed(&bar_acc_empty[ab], (uint32_t)((ti >> 1) - 1) & 1u, dbg, w_acc);
           tc_fence_after();
         }
         const uint32_t d_tmem = tmem_base + (uint32_t)(ab * n_pad);
         for (int kc = 0; kc < n_chunks; ++kc, ++item) {
           const int st = (int)(item % n_stages);
-          mbar_wait(&bar_full[st], (uint32_t)(item / n_stages) & 1u);
+          mbar_wait_timed(&bar_full[st], (uint32_t)(item / n_stages) & 1u, dbg, w_full);
           tc_fence_after();
           const uint32_t a_hi = sA_addr + st * Cfg::A_STAGE_BYTES;
           const uint32_t a_lo = a_hi + Cfg::PART_BYTES;
@@ -337,62 +389,116 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const DenseArgs
               umma<MODE>(d_tmem, da_hi, db_lo, idesc, 1u);
             }
           }
-          umma_commit(&bar_empty[st]);
+          umma_commit(&bar_done[item % n_done]);
           if (kc == n_chunks - 1) umma_commit(&bar_acc_full[ab]);
         }
       }
+      if (dbg && blockIdx.x == 0) {
+        dbg[2] = (unsigned long long)(clock64() - t_role0);
+        dbg[3] = w_full;
+        dbg[4] = w_acc;
+      }
     }
-  } else if (warp < 4) {
+  } else if (warp < EPI_WARPS) {
     // ================= epilogue: TMEM -> registers -> bias / accumulate / activation / row scale -> global =================
-    const int row_in_tile = warp * 32 + lane;  // TMEM lane == tile row; warp w may touch lanes 32 w .. 32 w + 31
-    // ReLU and identity share one branch-free path (max with 0 or -inf); sigmoid is a separate loop
+    const int quarter = warp & 3, half = warp >> 2;  // a warp may touch TMEM lanes 32 (warp % 4) .. + 31
+    const int row_in_tile = quarter * 32 + lane;      // TMEM lane == tile row
+    // ReLU and identity share one branch-free path (max with 0 or -inf); sigmoid is out of line
     const float lower = a.act_fn == XPGNN_ACT_RELU ? 0.0f : -INFINITY;
     const bool vec_ok = (a.n_out & 3) == 0 && (a.ld_out & 3) == 0 && (a.out_s_stride & 3) == 0 && (a.out_chunk_stride & 3) == 0;
+    float* s_t = s_tr + warp * (32 * TR_STRIDE);  // this warp's transposition block
+    unsigned long long w_accfull = 0;
+    const long long t_role0 = clock64();
+    // tile-table entry / row scale of this thread's row, fetched one tile ahead (a DRAM round trip otherwise exposed per tile)
+    int32_t nxt_e = -1;
+    float nxt_rs = 1.0f;
+    auto fetch_entry = [&](int64_t ti_) {
+      const int64_t pos = ((int64_t)blockIdx.x + ti_ * gridDim.x) * 128 + row_in_tile;
+      nxt_e = __ldg(a.rows_packed + pos);
+      nxt_rs = a.rs_packed ? __ldg(a.rs_packed + pos) : 1.0f;
+    };
+    if (a.rows_packed && my_tiles > 0) fetch_entry(0);
     for (int64_t ti = 0; ti < my_tiles; ++ti) {
       const int ab = (int)(ti & 1);
       const int64_t tile = (int64_t)blockIdx.x + ti * gridDim.x;
-      DenseRow row;
-      const bool ok = dense_resolve_row(a, tile, row_in_tile, row);
-      const int64_t oo = row.oo;
-      const float rs = row.rs;
-      mbar_wait(&bar_acc_full[ab], (uint32_t)(ti >> 1) & 1u);
+      bool ok;
+      int64_t oo;
+      float rs;
+      if (a.rows_packed) {
+        const int32_t e = nxt_e;
+        ok = e >= 0;
+        rs = nxt_rs;
+        oo = ok ? (int64_t)((uint32_t)e >> kPackShift) * a.out_s_stride + (int64_t)(e & ((1 << kPackShift) - 1)) * a.ld_out : -1;
+        if (ti + 1 < my_tiles) fetch_entry(ti + 1);
+      } else {
+        DenseRow row;
+        ok = dense_resolve_row(a, tile, row_in_tile, row);
+        oo = ok ? row.oo : -1;
+        rs = row.rs;
+      }
+      // after the transposition lane l writes 16 bytes of rows 8 i + l / 4 (i = 0..3): fetch their offsets once per tile
+      int64_t oo_r[4];
+      float rs_r[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        oo_r[i] = __shfl_sync(0xffffffffu, oo, i * 8 + (lane >> 2));
+        rs_r[i] = __shfl_sync(0xffffffffu, rs, i * 8 + (lane >> 2));
+      }
+      mbar_wait_timed(&bar_acc_full[ab], (uint32_t)(ti >> 1) & 1u, dbg, w_accfull);
       tc_fence_after();
-      for (int c0 = 0; c0 < n_pad; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ab * n_pad + c0), r);
-        if (!ok) continue;
+      for (int c0 = half * 16; c0 < n_pad; c0 += 32) {
+        uint32_t r[16];
+        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * n_pad + c0), r);
+        // A thread owns one accumulator row; storing it directly would touch 32 different lines per store
+        // instruction.  Transpose 32 x 16 blocks through shared memory: 4 lanes then write one 64-byte run
+        // of a row, 8 rows per instruction.
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 16; c += 4)
+          *reinterpret_cast<uint4*>(s_t + lane * TR_STRIDE + c) = make_uint4(r[c], r[c + 1], r[c + 2], r[c + 3]);
+        __syncwarp();
         if (vec_ok) {
-          float4 prev[8];
-          if (a.accumulate) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c)
-              prev[c] = (c0 + 4 * c < a.n_out) ? *reinterpret_cast<const float4*>(a.out + oo + dense_out_off(a, c0 + 4 * c))
-                                               : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-#pragma unroll
-          for (int c = 0; c < 32; c += 4) {
-            const int n = c0 + c;
-            if (n >= a.n_out) break;
+          const int cq = (lane & 3) * 4, n = c0 + cq;
+          if (n < a.n_out) {
             const float4 bb = *reinterpret_cast<const float4*>(s_bias + n);
-            float4 v = make_float4(__uint_as_float(r[c]) + bb.x, __uint_as_float(r[c + 1]) + bb.y, __uint_as_float(r[c + 2]) + bb.z,
-                                   __uint_as_float(r[c + 3]) + bb.w);
+            const int64_t ooff = dense_out_off(a, n);
+            float4 v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const float4*>(s_t + (i * 8 + (lane >> 2)) * TR_STRIDE + cq);
             if (a.accumulate) {
-              v.x += prev[c >> 2].x; v.y += prev[c >> 2].y; v.z += prev[c >> 2].z; v.w += prev[c >> 2].w;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                if (oo_r[i] < 0) continue;
+                const float4 pv = *reinterpret_cast<const float4*>(a.out + oo_r[i] + ooff);
+                v[i].x += pv.x; v[i].y += pv.y; v[i].z += pv.z; v[i].w += pv.w;
+              }
             }
-            if (a.act_fn == XPGNN_ACT_SIGMOID) {
-              sigmoid4(v);
-            } else {
-              v.x = fmaxf(v.x, lower); v.y = fmaxf(v.y, lower); v.z = fmaxf(v.z, lower); v.w = fmaxf(v.w, lower);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {  // branch free up to the (predicated) store
+              v[i].x += bb.x; v[i].y += bb.y; v[i].z += bb.z; v[i].w += bb.w;
+              if (a.act_fn == XPGNN_ACT_SIGMOID) {
+                v[i] = sigmoid4(v[i]);
+              } else {
+                v[i].x = fmaxf(v[i].x, lower); v[i].y = fmaxf(v[i].y, lower); v[i].z = fmaxf(v[i].z, lower); v[i].w = fmaxf(v[i].w, lower);
+              }
+              v[i].x *= rs_r[i]; v[i].y *= rs_r[i]; v[i].z *= rs_r[i]; v[i].w *= rs_r[i];
             }
-            v.x *= rs; v.y *= rs; v.z *= rs; v.w *= rs;
-            *reinterpret_cast<float4*>(a.out + oo + dense_out_off(a, n)) = v;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (oo_r[i] >= 0) *reinterpret_cast<float4*>(a.out + oo_r[i] + ooff) = v[i];
           }
-        } else {
-          scalar_epilogue(a, r, c0, oo, rs, s_bias);
+        } else if (ok) {
+          scalar_epilogue(s_t + lane * TR_STRIDE, c0, a.n_out, s_bias, a.out + oo, a.cw_out, a.cw_out_lg, a.out_chunk_stride, a.accumulate,
+                          a.act_fn, rs);
         }
       }
       tc_fence_before();
       mbar_arrive(&bar_acc_empty[ab]);
+    }
+    if (dbg && blockIdx.x == 0 && tid == 0) {
+      dbg[5] = (unsigned long long)(clock64() - t_role0);
+      dbg[6] = w_accfull;
+      dbg[7] = (unsigned long long)my_tiles;
     }
   }
   tc_fence_before();
@@ -407,7 +513,7 @@ static size_t tc_b_bytes(const DenseArgs& d, int mode) {
 }
 static int tc_stages(const DenseArgs& d, int mode) {
   const size_t stage = mode == 0 ? TcCfg<0>::A_STAGE_BYTES : TcCfg<1>::A_STAGE_BYTES;
-  const size_t budget = 200 * 1024;
+  const size_t budget = 204 * 1024;  // + ~22 KB static (transposition blocks, bias, barriers) < 227 KB
   const size_t b = tc_b_bytes(d, mode);
   if (b + 2 * stage > budget) return 0;
   return (int)std::min<size_t>(MAX_STAGES, (budget - b) / stage);
@@ -430,12 +536,27 @@ int launch_dense_tc(const DenseArgs& d, int mode, cudaStream_t st) {
   const size_t smem = tc_b_bytes(d, mode) + (size_t)stages * (mode == 0 ? TcCfg<0>::A_STAGE_BYTES : TcCfg<1>::A_STAGE_BYTES);
   const int64_t tiles = ceil_div(d.M, TM);
   const int grid = (int)std::min<int64_t>(tiles, kNumSMs);
+  // XPGNN_DENSE_DBG=1: per-role cycle counters of CTA 0 (synchronises; diagnostics only)
+  static const bool dbg_on = getenv("XPGNN_DENSE_DBG") != nullptr;
+  unsigned long long* dbg = nullptr;
+  if (dbg_on) {
+    XP_CHECK(cudaMalloc(&dbg, 8 * sizeof(unsigned long long)));
+    XP_CHECK(cudaMemsetAsync(dbg, 0, 8 * sizeof(unsigned long long), st));
+  }
   if (mode == 0) {
     XP_CHECK(cudaFuncSetAttribute(dense_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    XP_LAUNCH(dense_tc_kernel<0>, grid, TC_THREADS, smem, st, d, n_pad, cols, stages);
+    XP_LAUNCH(dense_tc_kernel<0>, grid, TC_THREADS, smem, st, d, n_pad, cols, stages, dbg);
   } else {
     XP_CHECK(cudaFuncSetAttribute(dense_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    XP_LAUNCH(dense_tc_kernel<1>, grid, TC_THREADS, smem, st, d, n_pad, cols, stages);
+    XP_LAUNCH(dense_tc_kernel<1>, grid, TC_THREADS, smem, st, d, n_pad, cols, stages, dbg);
+  }
+  if (dbg_on) {
+    unsigned long long h[8];
+    XP_CHECK(cudaStreamSynchronize(st));
+    XP_CHECK(cudaMemcpy(h, dbg, sizeof h, cudaMemcpyDeviceToHost));
+    XP_CHECK(cudaFree(dbg));
+    fprintf(stderr, "[dense_tc] tiles/CTA %llu stages %d | loader total %llu wait_empty %llu | mma total %llu wait_full %llu wait_acc_empty %llu | epilogue total %llu wait_acc_full %llu (cycles)\n",
+            h[7], stages, h[0], h[1], h[2], h[3], h[4], h[5], h[6]);
   }
   return 0;
 }

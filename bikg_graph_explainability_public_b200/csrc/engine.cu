@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(256) dense_rows_kernel(const DenseArgs a) {
   __shared__ float row_scale[DBM];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int64_t tile = blockIdx.x >> 1;  // 128-row tile of the shared row naming (dense_args.cuh); this CTA takes one half
-  if (a.tile_map && tile >= *a.n_tiles_dev) return;
+  if (a.rows_packed && tile >= *a.n_tiles_dev) return;
   const int n0 = blockIdx.y * DBN;
   if (tid < DBM) {
     DenseRow row;
