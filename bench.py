@@ -3,7 +3,9 @@
 
 Workload (config.workload = "c3"): BASELINE.json configs[2] -- synthetic homogeneous graph, 1 M nodes /
 20 M edges (uniform), 2 x GCNConv(128) + Linear(128 -> 1), 500 disjoint communities, whole-graph
-computational graph, every conv layer on every row ("full" mode = the work the reference does).
+computational graph, every conv layer over the whole graph ("full" mode = the work the reference does; the
+engine only materialises, per coalition, the rows of its ACTIVE nodes -- an inactive node has no active
+in-edge, so its row is coalition invariant and never gathered).
 A step = one pass of the hot path over one batch of synthetic coalitions: each rank evaluates
 `--coalitions-per-gpu` (default 512) coalition rows, so that 8 ranks x 512 = the 4096-coalition job of
 the north star in one step (weak scaling: per-GPU work fixed).
@@ -11,8 +13,9 @@ the north star in one step (weak scaling: per-GPU work fixed).
 value   : coalition evals/s, masks/graph/weights resident in HBM, CUDA-event timed, max over ranks.
 e2e     : same metric through the public API with HOST coalition masks: pinned (B, N) uint8 rows ->
           H2D -> bit packing -> masked forward -> D2H of the predictions, all inside the timed region.
-roofline: masked SpMM on coalition-specific activations (layers >= 1), algorithmic bytes per launch
-           / CUDA-event kernel time measured live via xpgnn_profile.
+roofline: masked SpMM on coalition-specific activations (layers >= 1, cspmm_kernel of csrc/compact.cu),
+          algorithmic bytes per launch (32 coalition-layers x 1.108 GB) / CUDA-event kernel
+          time measured live via xpgnn_profile (events on the launching stream).
 cpu_baseline / --impl reference: the oracle port of the reference algorithm (block-diagonal
           materialisation, in1d edge filter, scatter-add GCN) on the host cores, bounded sample.
 """
@@ -168,8 +171,9 @@ def run_reference(args, rank):
 
 def config_dict(args, n, e, h, c):
     return {"workload": args.workload, "nodes": n, "edges": e, "model": "2xGCNConv(%d)+Linear(%d,1)" % (h, h),
-            "communities": c, "coalitions_per_gpu_per_step": args.coalitions_per_gpu, "mode": "full (every conv layer on "
-            "every row of the whole-graph computational graph)", "l2": "inputs larger than L2 (activation tiles of "
+            "communities": c, "coalitions_per_gpu_per_step": args.coalitions_per_gpu, "mode": "full (every conv layer "
+            "over the whole-graph computational graph; per coalition only rows of active nodes are materialised, "
+            "inactive rows are coalition invariant)", "l2": "inputs larger than L2 (activation tiles of "
             "16 GiB vs 126 MB L2)", "precision": getattr(args, "precision", "fp32") + (
                 " (fp32 storage, dense transforms as 3xTF32 tcgen05 MMAs)" if getattr(args, "precision", "fp32") == "fp32"
                 else " transforms (fp32 storage, bf16 tcgen05 MMAs, fp32 accumulate)")}
@@ -314,6 +318,7 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         dom = "spmm_tile_l1" if kern["spmm_tile_l1"]["ms"] >= kern["spmm_invariant_l0"]["ms"] else "spmm_invariant_l0"
+        share = {k: v["ms"] / max(sum(x["ms"] for x in kern.values()), 1e-9) for k, v in kern.items()}
         tile = eng.tile_coalitions
         roof = {}
         for k in ("spmm_tile_l1", "spmm_invariant_l0"):
@@ -338,13 +343,14 @@ def main():
                     "h2d_bytes_per_step": int(mask_host.numel()), "d2h_bytes_per_step": int(y_host.numel() * 4)},
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
-            "roofline": {"bound": "hbm", "kernel": "spmm_masked_kernel (%s)" % dom,
+            "roofline": {"bound": "hbm", "kernel": "cspmm_kernel (%s)" % dom,
                          "achieved": roof.get(dom, {}).get("achieved_gbs"), "peak": peak, "unit": "GB/s",
                          "frac": roof.get(dom, {}).get("frac"), "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                          "algorithmic_bytes_per_launch": tile * b_alg, "coalitions_per_launch": tile,
                          "per_kernel": roof},
             "kernels": kern,
+            "kernel_share_of_step": share,
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, n, f, h, x, ei, arch, mask_host, q, y_host)
