@@ -36,15 +36,27 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # name: (nodes, edges, features, hidden, communities)
     "c3": (1_000_000, 20_000_000, 128, 128, 500),
+    "c3_rmat": (1_000_000, 20_000_000, 128, 128, 500),  # R-MAT(0.57, 0.19, 0.19, 0.05): hub rows
     "c3_tenth": (100_000, 2_000_000, 128, 128, 50),
     "tiny": (20_000, 400_000, 32, 32, 20),
 }
 
 
+def rmat_edges(n, e, g, a=0.57, b=0.19, c=0.19):
+    bits = int(np.ceil(np.log2(n)))
+    src = torch.zeros(e, dtype=torch.int64)
+    dst = torch.zeros(e, dtype=torch.int64)
+    for _ in range(bits):
+        r = torch.rand(e, generator=g)
+        src = src * 2 + (r >= a + b).to(torch.int64)                                # quadrants c, d
+        dst = dst * 2 + (((r >= a) & (r < a + b)) | (r >= a + b + c)).to(torch.int64)  # quadrants b, d
+    return torch.stack([src % n, dst % n])
+
+
 def make_graph(name):
     n, e, f, h, c = WORKLOADS[name]
     g = torch.Generator().manual_seed(1234)
-    ei = torch.randint(0, n, (2, e), generator=g)
+    ei = rmat_edges(n, e, g) if name.endswith("_rmat") else torch.randint(0, n, (2, e), generator=g)
     x = torch.randn(n, f, generator=g)
     com_of = torch.randperm(n, generator=g) % c  # c disjoint, equal communities
     return n, e, f, h, c, x, ei, com_of

@@ -197,21 +197,39 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
-// A warp owns one destination row and walks its 64-column blocks.  The 32 lanes tile the (32 slots x 64 columns)
-// accumulator block 4 x 8: lane = 8 sg + cg owns slots 8 sg .. 8 sg + 7 and columns 8 cg .. 8 cg + 7 (64 registers).
-// Per batch of <= 32 in-edges:
+// A warp owns one destination row and walks its 64-column blocks; a lane owns 2 columns of the block and the
+// accumulators of the row's ACTIVE slots (the slots in which the destination node is inactive produce nothing:
+// about half of them), at most 32 float2 = 64 registers.  Per batch of <= 32 in-edges:
 //   weights : lane j loads the 32 per-slot scales of source u_j (8 independent 128-bit loads), zeroes the
-//             slots in which edge j is inactive and stores the row to shared memory (once per row);
+//             slots in which edge j is inactive, stores the row to shared memory and compacts it in place to
+//             the destination's active slots (k-th active slot -> position k), once per row;
 //   operand : the 256-byte pieces of Z[u_j] go to shared memory with cp.async, all in flight together;
-//   FMAs    : per edge 2 LDS.128 (weights of the lane's slots) + 2 LDS.128 (z of its columns) + 64 FFMA,
-//             unconditional (a zero weight is cheaper than a branch).
+//   FMAs    : per edge 1 LDS.64 (z) + NQ broadcast LDS.128 (weights) + 8 NQ FFMA, NQ = ceil(active slots / 4)
+//             a compile-time constant of the specialised loop (a zero weight is cheaper than a branch).
+template <int NQ>
+__device__ __forceinline__ void l0_fma(const float* __restrict__ w_rows, const float* __restrict__ z_rows, int n, int lane, float2 (&acc)[32]) {
+#pragma unroll 1
+  for (int j = 0; j < n; ++j) {
+    const float2 zv = *reinterpret_cast<const float2*>(z_rows + j * 64 + lane * 2);
+    const float4* wr = reinterpret_cast<const float4*>(w_rows + j * kL0WStride);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const float4 w4 = wr[q];
+      acc[4 * q + 0].x = fmaf(w4.x, zv.x, acc[4 * q + 0].x); acc[4 * q + 0].y = fmaf(w4.x, zv.y, acc[4 * q + 0].y);
+      acc[4 * q + 1].x = fmaf(w4.y, zv.x, acc[4 * q + 1].x); acc[4 * q + 1].y = fmaf(w4.y, zv.y, acc[4 * q + 1].y);
+      acc[4 * q + 2].x = fmaf(w4.z, zv.x, acc[4 * q + 2].x); acc[4 * q + 2].y = fmaf(w4.z, zv.y, acc[4 * q + 2].y);
+      acc[4 * q + 3].x = fmaf(w4.w, zv.x, acc[4 * q + 3].x); acc[4 * q + 3].y = fmaf(w4.w, zv.y, acc[4 * q + 3].y);
+    }
+  }
+}
+
 template <bool SIGMOID>
 __global__ void __launch_bounds__(256, 2) l0_rows_kernel(const L0RowsArgs a) {
   extern __shared__ __align__(16) uint8_t l0_smem[];
   float(*s_w)[32][kL0WStride] = reinterpret_cast<float(*)[32][kL0WStride]>(l0_smem);
   float(*s_z)[32][64] = reinterpret_cast<float(*)[32][64]>(l0_smem + 8 * 32 * kL0WStride * 4);
   int(*s_u)[32] = reinterpret_cast<int(*)[32]>(l0_smem + 8 * 32 * kL0WStride * 4 + 8 * 32 * 64 * 4);
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, sg = lane >> 3, cg = lane & 7;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint32_t live = (a.nb == 32 ? 0xffffffffu : ((1u << a.nb) - 1u)) << a.b0;  // bits of the word in this tile
   const bool gcn = a.kind == XPGNN_CONV_GCN;
   const int ncb = a.h0 / 64;
@@ -219,15 +237,14 @@ __global__ void __launch_bounds__(256, 2) l0_rows_kernel(const L0RowsArgs a) {
   for (int v = blockIdx.x * 8 + wib; v < a.N; v += gridDim.x * 8) {
     const uint32_t av = a.act[(int64_t)v * a.W + a.w] & live;
     if (!av) continue;
+    const int n_slots = __popc(av), nq = (n_slots + 3) >> 2;
     const int e0 = a.rowptr[v], e1 = a.rowptr[v + 1];
     const bool short_row = e1 - e0 <= 32;
     const float sc_v = a.scale[(int64_t)v * 32 + lane];
     for (int cb = 0; cb < ncb; ++cb) {
-      float acc[8][8];
+      float2 acc[32];
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
-#pragma unroll
-        for (int c = 0; c < 8; ++c) acc[k][c] = 0.0f;
+      for (int k = 0; k < 32; ++k) acc[k] = make_float2(0.f, 0.f);
       for (int base = e0; base < e1; base += 32) {
         const int n = min(32, e1 - base);
         __syncwarp();
@@ -236,6 +253,7 @@ __global__ void __launch_bounds__(256, 2) l0_rows_kernel(const L0RowsArgs a) {
             const int u = __ldg(a.col + base + lane);
             const uint32_t bits = __ldg(a.ebits + base + lane) & av;
             s_u[wib][lane] = u;
+            float* wrow = &s_w[wib][lane][0];
             float4 wq[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q)
@@ -246,8 +264,12 @@ __global__ void __launch_bounds__(256, 2) l0_rows_kernel(const L0RowsArgs a) {
               wq[q].y = (bits >> (4 * q + 1)) & 1u ? wq[q].y : 0.0f;
               wq[q].z = (bits >> (4 * q + 2)) & 1u ? wq[q].z : 0.0f;
               wq[q].w = (bits >> (4 * q + 3)) & 1u ? wq[q].w : 0.0f;
-              *reinterpret_cast<float4*>(&s_w[wib][lane][4 * q]) = wq[q];
+              *reinterpret_cast<float4*>(wrow + 4 * q) = wq[q];
             }
+            // in place: position k <- bit b_k (k <= b_k and the bits ascend, so nothing unread is overwritten)
+            int k = 0;
+            for (uint32_t m = av; m; m &= m - 1, ++k) wrow[k] = wrow[__ffs(m) - 1];
+            for (; k < 4 * nq; ++k) wrow[k] = 0.0f;
           }
           __syncwarp();
         }
@@ -258,56 +280,50 @@ __global__ void __launch_bounds__(256, 2) l0_rows_kernel(const L0RowsArgs a) {
         }
         cp_async_wait_all();
         __syncwarp();
-#pragma unroll 1
-        for (int j = 0; j < n; ++j) {
-          const float4 w0 = *reinterpret_cast<const float4*>(&s_w[wib][j][sg * 8]);
-          const float4 w1 = *reinterpret_cast<const float4*>(&s_w[wib][j][sg * 8 + 4]);
-          const float4 z0 = *reinterpret_cast<const float4*>(&s_z[wib][j][cg * 8]);
-          const float4 z1 = *reinterpret_cast<const float4*>(&s_z[wib][j][cg * 8 + 4]);
-          const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-          const float z[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-#pragma unroll
-            for (int c = 0; c < 8; ++c) acc[k][c] = fmaf(w[k], z[c], acc[k][c]);
+        const float* wr = &s_w[wib][0][0];
+        const float* zr = &s_z[wib][0][0];
+        switch (nq) {
+          case 1: l0_fma<1>(wr, zr, n, lane, acc); break;
+          case 2: l0_fma<2>(wr, zr, n, lane, acc); break;
+          case 3: l0_fma<3>(wr, zr, n, lane, acc); break;
+          case 4: l0_fma<4>(wr, zr, n, lane, acc); break;
+          case 5: l0_fma<5>(wr, zr, n, lane, acc); break;
+          case 6: l0_fma<6>(wr, zr, n, lane, acc); break;
+          case 7: l0_fma<7>(wr, zr, n, lane, acc); break;
+          default: l0_fma<8>(wr, zr, n, lane, acc); break;
         }
       }
-      // ---- epilogue of the column block: the lane's 8 columns are 32 contiguous bytes of chunk 2 cb + cg / 4 ----
-      const float* zs = a.z + (int64_t)v * a.h0 + cb * 64 + cg * 8;
-      float self[8], add[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) { self[c] = 0.0f; add[c] = 0.0f; }
-      if (gcn) {
-        const float4 s0 = __ldg(reinterpret_cast<const float4*>(zs)), s1 = __ldg(reinterpret_cast<const float4*>(zs + 4));
-        self[0] = s0.x; self[1] = s0.y; self[2] = s0.z; self[3] = s0.w; self[4] = s1.x; self[5] = s1.y; self[6] = s1.z; self[7] = s1.w;
-      }
-      if (a.bias) {
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.bias + cb * 64 + cg * 8)), b1 = __ldg(reinterpret_cast<const float4*>(a.bias + cb * 64 + cg * 8 + 4));
-        add[0] = b0.x; add[1] = b0.y; add[2] = b0.z; add[3] = b0.w; add[4] = b1.x; add[5] = b1.y; add[6] = b1.z; add[7] = b1.w;
-      }
-      const int64_t cm_off = (int64_t)(cb * 2 + (cg >> 2)) * a.out_chunk_stride + (int64_t)v * 32 + (cg & 3) * 8;
+      // ---- epilogue of the column block: position k of the accumulators is the k-th active slot ----
+      const float* zs = a.z + (int64_t)v * a.h0 + cb * 64 + lane * 2;
+      float2 self = make_float2(0.f, 0.f), add = self;
+      if (gcn) self = __ldg(reinterpret_cast<const float2*>(zs));
+      if (a.bias) add = __ldg(reinterpret_cast<const float2*>(a.bias + cb * 64 + lane * 2));
+      const int64_t cm_off = (int64_t)(cb * 2 + (lane >> 4)) * a.out_chunk_stride + (int64_t)v * 32 + (lane & 15) * 2;
       if (a.r0c) {
-        const float* rp = a.r0c + (int64_t)(cb * 2 + (cg >> 2)) * a.r0_chunk_stride + (int64_t)v * 32 + (cg & 3) * 8;
-        const float4 r0 = __ldg(reinterpret_cast<const float4*>(rp)), r1 = __ldg(reinterpret_cast<const float4*>(rp + 4));
-        add[0] += r0.x; add[1] += r0.y; add[2] += r0.z; add[3] += r0.w; add[4] += r1.x; add[5] += r1.y; add[6] += r1.z; add[7] += r1.w;
+        const float2 r = __ldg(reinterpret_cast<const float2*>(a.r0c + (int64_t)(cb * 2 + (lane >> 4)) * a.r0_chunk_stride + (int64_t)v * 32 + (lane & 15) * 2));
+        add.x += r.x; add.y += r.y;
       }
       // kept tiny (the kernel must stay inside the instruction cache): GCN and SAGE share one formula
       // (SAGE: self weight 0), ReLU / identity are a max with 0 / -inf
-      float* outp = a.out + cm_off + (int64_t)(sg * 8 - a.b0) * a.out_s_stride;
+      float* outp = a.out + cm_off - (int64_t)a.b0 * a.out_s_stride;
+      uint32_t m = av;
 #pragma unroll
-      for (int k = 0; k < 8; ++k, outp += a.out_s_stride) {
-        const float dv = __shfl_sync(0xffffffffu, sc_v, sg * 8 + k);
-        if ((av >> (sg * 8 + k)) & 1u) {
+      for (int k = 0; k < 32; ++k) {
+        if (k < n_slots) {  // warp uniform
+          const int b = __ffs(m) - 1;
+          m &= m - 1;
+          const float dv = __shfl_sync(0xffffffffu, sc_v, b);
           const float sw = gcn ? dv : 0.0f, pv = a.prescale ? dv : 1.0f;
-          float o[8];
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            o[c] = dv * fmaf(self[c], sw, acc[k][c]) + add[c];
-            o[c] = SIGMOID ? apply_act(o[c], XPGNN_ACT_SIGMOID) : fmaxf(o[c], lower);
-            o[c] *= pv;
+          float2 o;
+          o.x = dv * fmaf(self.x, sw, acc[k].x) + add.x;
+          o.y = dv * fmaf(self.y, sw, acc[k].y) + add.y;
+          if (SIGMOID) {
+            o.x = apply_act(o.x, XPGNN_ACT_SIGMOID); o.y = apply_act(o.y, XPGNN_ACT_SIGMOID);
+          } else {
+            o.x = fmaxf(o.x, lower); o.y = fmaxf(o.y, lower);
           }
-          __stcs(reinterpret_cast<float4*>(outp), make_float4(o[0], o[1], o[2], o[3]));
-          __stcs(reinterpret_cast<float4*>(outp + 4), make_float4(o[4], o[5], o[6], o[7]));
+          o.x *= pv; o.y *= pv;
+          __stcs(reinterpret_cast<float2*>(outp + (int64_t)b * a.out_s_stride), o);
         }
       }
     }

@@ -92,11 +92,14 @@ class Data:
         subset, sub_ei, sub_ind, edge_mask, hop, _ = khop_subgraph(self.edge_index, n, ind, n_hops)
         self.last_hop = hop[subset]
         sub_feat = self.feat.to(subset.device)[subset]
-        names_array = np.array(names, dtype=str)
         sub_nt = node_types.to(subset.device)[subset] if node_types is not None else None
         sub_et = edge_types.to(subset.device)[edge_mask] if edge_types is not None else None
         if ("node" in problem) or ("graph" in problem):
-            sub_names = names_array[subset.cpu().numpy()].tolist()
+            idx = subset.cpu().tolist()
+            if all(type(x) is str for x in names):
+                sub_names = [names[i] for i in idx]  # == np.array(names, dtype=str)[subset].tolist(), without the N-string array
+            else:
+                sub_names = np.array(names, dtype=str)[idx].tolist()
         else:
             raise NotImplementedError("edge problems are outside the accelerated path (SURVEY.md 8f-4)")
         return sub_feat, sub_ei, sub_names, sub_ind, sub_nt, sub_et

@@ -135,6 +135,8 @@ class Explainer:
             ), "No element names have been given and the node name given is not numeric"
             return int(element)
         assert element in names, "Element name '{}' is not present in the graph".format(element)
+        if type(element) is str and all(type(x) is str for x in names):
+            return names.index(element)  # first match, as np.where(...)[0][0]
         return int(np.where(np.array(names, dtype=str) == element)[0][0])
 
     def filter_hetero_names(self, names, node_type, edge_type, node_type_names, edge_type_names):

@@ -1,8 +1,12 @@
 """Community bookkeeping behind the reference's ``Pathways`` interface (``pathways.py:8-429``).
 
-Name resolution stays on the host exactly as in the reference (numpy string ``intersect1d``;
-SURVEY.md 8f-1 lists the integer-id fast path as the next widening step); the community-level
-random masks live in ``masks.py`` (device), and ``aggregate`` runs the segmented-mean kernel.
+Name resolution is host work, as in the reference, but not the reference's algorithm: it calls
+``np.intersect1d(community, names)`` once per community, i.e. sorts the whole name array C times
+(O(C N log N) string compares -- 60 s of a 70 s query at 1 M nodes / 500 communities).  Here one
+name -> first-index hash map is built per call and every community is filtered / deduplicated /
+sorted on its own (O(N + sum L log L)); the outputs are identical (``tests/test_capi_and_host.py``
+checks them against the ``intersect1d`` formulation) -- SURVEY.md 8f-1.  The community-level random
+masks live in ``masks.py`` (device), and ``aggregate`` runs the segmented-mean kernel.
 """
 import itertools
 
@@ -14,6 +18,22 @@ from . import _lib
 from .engine import require_cuda
 
 
+def _as_str(values):
+    """``np.array(values, dtype=str)`` element-wise: strings pass through, everything else via numpy's conversion."""
+    if all(type(v) is str for v in values):
+        return values
+    return np.array(values, dtype=str).tolist()
+
+
+def _first_index(names):
+    """name -> index of its first occurrence (``np.unique(..., return_index=True)`` semantics)."""
+    first = {}
+    for i, name in enumerate(_as_str(names)):
+        if name not in first:
+            first[name] = i
+    return first
+
+
 class Pathways:
     def __init__(self, communities, community_names, community_types=None):
         self.communities = communities
@@ -23,14 +43,15 @@ class Pathways:
             self.community_names = np.arange(len(self.communities)).tolist()
 
     def comp_graph(self, names):
-        """pathways.py:33-102: keep communities with at least one member in the subgraph."""
-        names_array = np.array(names, dtype=str)
+        """pathways.py:33-102: keep communities with at least one member in the subgraph.
+        Members come back as the sorted unique *names* present in ``names`` (what ``intersect1d`` returns)."""
+        present = _first_index(names)
         sub, sub_names = [], []
         sub_types = [] if self.community_types is not None else None
         for i, (community, cname) in enumerate(zip(self.communities, self.community_names)):
-            common = np.intersect1d(np.array(community, dtype=str), names_array)
+            common = sorted({m for m in _as_str(community) if m in present})
             if len(common) > 0:
-                sub.append(common.tolist())
+                sub.append(common)
                 sub_names.append(cname)
                 if sub_types is not None:
                     sub_types.append(self.community_types[i])
@@ -42,11 +63,11 @@ class Pathways:
         """pathways.py:104-136: member names -> subgraph indices, in lexicographic name order."""
         if isinstance(self.communities[0][0], int):
             return self.communities
-        names_array = np.array(names, dtype=str)
+        first = _first_index(names)
         inds = []
         for community in self.communities:
-            _, ind, _ = np.intersect1d(names_array, np.array(community, dtype=str), return_indices=True)
-            inds.append(ind.tolist())
+            common = sorted({m for m in _as_str(community) if m in first})
+            inds.append([first[m] for m in common])  # intersect1d(return_indices): first occurrence, name order
         return inds
 
     def shift_hetero_pathways(self, pointers):

@@ -171,3 +171,45 @@ def test_word_range_partitions_tiles():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _pathways_numpy_formulation(communities, names):
+    """The reference's algorithm (pathways.py:84-96, 131-134): intersect1d against the whole name array per community."""
+    names_array = np.array(names, dtype=str)
+    sub, inds = [], []
+    for community in communities:
+        common = np.intersect1d(np.array(community, dtype=str), names_array)
+        if len(common) > 0:
+            sub.append(common.tolist())
+    for community in sub:
+        _, ind, _ = np.intersect1d(names_array, np.array(community, dtype=str), return_indices=True)
+        inds.append(ind.tolist())
+    return sub, inds
+
+
+@pytest.mark.parametrize("case", ["str", "int_members", "duplicates", "unicode"])
+def test_name_resolution_fast_path_equals_intersect1d(case):
+    """the hash-map name resolution returns exactly what the reference's per-community
+    ``np.intersect1d`` returns (members as sorted unique names, indices of first occurrences in name order)."""
+    from bikg_graph_explainability_public_b200.pathways import Pathways
+
+    rng = np.random.default_rng(3)
+    n = 500
+    if case == "unicode":
+        names = ["gène_%d" % i if i % 3 else "Ωmega%d" % i for i in range(n)]
+    else:
+        names = [str(i) for i in range(n)]
+    sub_names = [names[i] for i in rng.permutation(n)[:300]]            # the computational graph keeps 300 nodes
+    if case == "duplicates":
+        sub_names = sub_names + sub_names[:25]                             # repeated names: first occurrence wins
+    communities = []
+    for c in range(12):
+        members = rng.integers(0, n, size=int(rng.integers(1, 60))).tolist()  # with repeats, partly outside the subgraph
+        communities.append(members if case == "int_members" else [names[i] for i in members])
+    communities.append([names[i] for i in range(n) if names[i] not in set(sub_names)][:5])  # dropped entirely
+    cnames = ["c%d" % i for i in range(len(communities))]
+    ref_sub, ref_inds = _pathways_numpy_formulation(communities, sub_names)
+    sub, sub_cnames, _ = Pathways(communities, cnames).comp_graph(sub_names)
+    assert sub == ref_sub
+    assert len(sub_cnames) == len(sub) == 12
+    assert Pathways(sub, sub_cnames).names2inds(sub_names) == ref_inds
