@@ -34,11 +34,19 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (nodes, edges, features, hidden, communities)
-    "c3": (1_000_000, 20_000_000, 128, 128, 500),
-    "c3_rmat": (1_000_000, 20_000_000, 128, 128, 500),  # R-MAT(0.57, 0.19, 0.19, 0.05): hub rows
-    "c3_tenth": (100_000, 2_000_000, 128, 128, 50),
-    "tiny": (20_000, 400_000, 32, 32, 20),
+    # BASELINE.json configs[2]: the configuration the metric is quoted on
+    "c3": dict(kind="homo_gcn", nodes=1_000_000, edges=20_000_000, features=128, hidden=128, communities=500),
+    # R-MAT(0.57, 0.19, 0.19, 0.05) variant of C3: hub rows
+    "c3_rmat": dict(kind="homo_gcn", nodes=1_000_000, edges=20_000_000, features=128, hidden=128, communities=500, rmat=True),
+    # configs[3]: biomedical-KG shape, 5 node types / 20 relations, 2 x HeteroConv(SAGEConv mean, sum)
+    "c4": dict(kind="hetero_sage", nodes=2_000_000, edges=50_000_000, features=64, hidden=128, communities=1000,
+               type_frac=(0.4, 0.25, 0.15, 0.1, 0.1), relations=20),
+    # configs[4]: scale sweep graph, 64 batched query nodes
+    "c5": dict(kind="homo_gcn", nodes=5_000_000, edges=100_000_000, features=128, hidden=128, communities=500, queries=64),
+    "c3_tenth": dict(kind="homo_gcn", nodes=100_000, edges=2_000_000, features=128, hidden=128, communities=50),
+    "c4_small": dict(kind="hetero_sage", nodes=40_000, edges=1_000_000, features=64, hidden=128, communities=40,
+                     type_frac=(0.4, 0.25, 0.15, 0.1, 0.1), relations=20),
+    "tiny": dict(kind="homo_gcn", nodes=20_000, edges=400_000, features=32, hidden=32, communities=20),
 }
 
 
@@ -53,38 +61,128 @@ def rmat_edges(n, e, g, a=0.57, b=0.19, c=0.19):
     return torch.stack([src % n, dst % n])
 
 
-def make_graph(name):
-    n, e, f, h, c = WORKLOADS[name]
-    g = torch.Generator().manual_seed(1234)
-    ei = rmat_edges(n, e, g) if name.endswith("_rmat") else torch.randint(0, n, (2, e), generator=g)
-    x = torch.randn(n, f, generator=g)
-    com_of = torch.randperm(n, generator=g) % c  # c disjoint, equal communities
-    return n, e, f, h, c, x, ei, com_of
+class Workload:
+    """Synthetic inputs of one BASELINE.json configuration, flattened to one node id space."""
 
+    def __init__(self, name):
+        w = WORKLOADS[name]
+        self.name, self.kind = name, w["kind"]
+        self.n, self.e, self.f, self.h, self.c = w["nodes"], w["edges"], w["features"], w["hidden"], w["communities"]
+        n, e = self.n, self.e
+        g = torch.Generator().manual_seed(1234)
+        self.type_ptr, self.node_type_names, self.edge_type, self.edge_type_names, self.node_type = [0, n], None, None, None, None
+        if self.kind == "homo_gcn":
+            self.ei = rmat_edges(n, e, g) if w.get("rmat") else torch.randint(0, n, (2, e), generator=g)
+            self.x = torch.randn(n, self.f, generator=g)
+            self.com_of = torch.randperm(n, generator=g) % self.c  # c disjoint, equal communities
+            q0 = 17
+            nq = w.get("queries", 1)
+            self.queries = [q0] if nq == 1 else torch.randperm(n, generator=g)[:nq].tolist()
+            self.q_in_type = self.queries[0]
+        else:
+            counts = [int(fr * n) for fr in w["type_frac"]]
+            counts[0] += n - sum(counts)
+            self.type_ptr = [0]
+            for cnt in counts:
+                self.type_ptr.append(self.type_ptr[-1] + cnt)
+            t = len(counts)
+            self.node_type_names = ["t%d" % i for i in range(t)]
+            pairs = [(i, i) for i in range(min(4, t))]  # >= 4 same-type relations
+            while len(pairs) < w["relations"]:
+                pairs.append((int(torch.randint(0, t, (1,), generator=g)), int(torch.randint(0, t, (1,), generator=g))))
+            self.edge_type_names = [("t%d" % a_, "rel%d" % i, "t%d" % b_) for i, (a_, b_) in enumerate(pairs)]
+            per = e // len(pairs)
+            eis, ets = [], []
+            for i, (a_, b_) in enumerate(pairs):
+                src = torch.randint(self.type_ptr[a_], self.type_ptr[a_ + 1], (per,), generator=g)
+                dst = torch.randint(self.type_ptr[b_], self.type_ptr[b_ + 1], (per,), generator=g)
+                eis.append(torch.stack([src, dst]))
+                ets.append(torch.full((per,), i, dtype=torch.int64))
+            self.ei, self.edge_type = torch.cat(eis, 1), torch.cat(ets)
+            self.e = int(self.ei.shape[1])
+            self.x = torch.randn(n, self.f, generator=g)
+            self.node_type = torch.cat([torch.full((cnt,), i, dtype=torch.float32) for i, cnt in enumerate(counts)])
+            # type-pure communities (the reference assumes them, README.md:218), sized by type
+            per_type = [max(1, round(self.c * cnt / n)) for cnt in counts]
+            per_type[0] += self.c - sum(per_type)
+            com_of, base = [], 0
+            for cnt, k in zip(counts, per_type):
+                com_of.append(base + torch.randperm(cnt, generator=g) % k)
+                base += k
+            self.com_of = torch.cat(com_of)
+            self.out_type = "t0"
+            self.q_in_type = 17
+            self.queries = [self.type_ptr[0] + self.q_in_type]
 
-def make_model(f, h, seed=7):
-    from torch import nn
+    @property
+    def model_name(self):
+        if self.kind == "homo_gcn":
+            return "2xGCNConv(%d)+Linear(%d,1)" % (self.h, self.h)
+        return "2xHeteroConv(%d x SAGEConv(%d, mean), sum)+Linear(%d,1)+Sigmoid" % (len(self.edge_type_names), self.h, self.h)
 
-    from bikg_graph_explainability_public_b200 import nn as xnn
+    def make_model(self, seed=7):
+        """Product-side weight containers (state-dict keys of the PyG layers)."""
+        from torch import nn
 
-    torch.manual_seed(seed)
+        from bikg_graph_explainability_public_b200 import nn as xnn
 
-    class GCN2(nn.Module):
-        def __init__(self):
-            super().__init__()
-            self.conv = nn.ModuleList([xnn.GCNConv(f, h), nn.ReLU(), xnn.GCNConv(h, h), nn.ReLU()])
-            self.fc = nn.ModuleList([xnn.Linear(h, 1)])
+        torch.manual_seed(seed)
+        f, h, wl = self.f, self.h, self
 
-    return GCN2().eval()
+        class GCN2(nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.conv = nn.ModuleList([xnn.GCNConv(f, h), nn.ReLU(), xnn.GCNConv(h, h), nn.ReLU()])
+                self.fc = nn.ModuleList([xnn.Linear(h, 1)])
 
+        class HeteroSAGE2(nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.out_type = wl.out_type
+                self.conv = nn.ModuleList([
+                    xnn.HeteroConv({r: xnn.SAGEConv((f, f), h) for r in wl.edge_type_names}), nn.ReLU(),
+                    xnn.HeteroConv({r: xnn.SAGEConv((h, h), h) for r in wl.edge_type_names}), nn.ReLU()])
+                self.fc = nn.ModuleList([xnn.Linear(h, 1), nn.Sigmoid()])
 
-def oracle_model(arch, f, h):
-    """Same weights in the oracle's CPU stand-in layers (for the CPU baseline / parity check)."""
-    from oracle import fixture_models as fm
+        return (GCN2() if self.kind == "homo_gcn" else HeteroSAGE2()).eval()
 
-    m = fm.HomoGCN(f, (h, h), (h, 1), final_sigmoid=False)
-    m.load_state_dict(arch.state_dict())
-    return m.eval()
+    def oracle_model(self, arch):
+        """Same weights in the oracle's CPU stand-in layers (for the CPU baseline / parity check)."""
+        from oracle import fixture_models as fm
+
+        if self.kind == "homo_gcn":
+            m = fm.HomoGCN(self.f, (self.h, self.h), (self.h, 1), final_sigmoid=False)
+        else:
+            m = fm.HeteroSAGE({t: self.f for t in self.node_type_names}, self.edge_type_names, self.out_type,
+                              conv_dims=(self.h, self.h), head_dims=(self.h, 1))
+        m.load_state_dict(arch.state_dict())
+        return m.eval()
+
+    def oracle_eval(self, om, mask_bool_np):
+        """Reference algorithm (oracle port) on the host: query prediction of every coalition row of ``mask``."""
+        from oracle.xpgnn_oracle import kernel_output
+
+        if self.kind == "homo_gcn":
+            _, y = kernel_output(mask_bool_np, self.x, self.ei.numpy(), om, self.queries[0])
+        else:
+            _, y = kernel_output(mask_bool_np, self.x, self.ei.numpy(), om, self.q_in_type, node_type=self.node_type,
+                                 edge_type=self.edge_type.numpy(), node_type_names=self.node_type_names,
+                                 edge_type_names=self.edge_type_names, padded_dims=[0] * len(self.node_type_names))
+        return y.numpy().reshape(-1)
+
+    def engine(self, dev, precision):
+        from bikg_graph_explainability_public_b200.engine import GraphSpec, MaskedForward
+        from bikg_graph_explainability_public_b200.lowering import lower
+
+        arch = self.make_model()
+        if self.kind == "homo_gcn":
+            g = GraphSpec(self.x.to(dev), self.ei.to(dev), [0, self.n])
+        else:
+            g = GraphSpec(self.x.to(dev), self.ei.to(dev), self.type_ptr, self.node_type_names, self.edge_type.to(dev),
+                          self.edge_type_names)
+        eng = MaskedForward(g, lower(arch), self.queries, prune=False, precision=precision,
+                            zero_edge_rule=self.kind != "homo_gcn")
+        return arch, eng
 
 
 def make_masks(n_rows, n, c, com_of, seed):
@@ -149,19 +247,15 @@ def run_reference(args, rank):
     """Reference arm: the oracle port of the reference's CPU algorithm, all host threads."""
     if rank != 0:
         return
-    from oracle.xpgnn_oracle import kernel_output
-
-    n, e, f, h, c, x, ei, com_of = make_graph(args.workload)
+    wl = Workload(args.workload)
     torch.set_num_threads(os.cpu_count())
-    arch = oracle_model(make_model(f, h), f, h)
+    om = wl.oracle_model(wl.make_model())
     b = args.ref_coalitions
-    mask = make_masks(b * (args.steps + args.warmup), n, c, com_of, 99).bool().numpy()
-    ei_np = ei.numpy()
-    q = 17
+    mask = make_masks(b * (args.steps + args.warmup), wl.n, wl.c, wl.com_of, 99).bool().numpy()
     times = []
     for i in range(args.steps + args.warmup):
         t0 = time.perf_counter()
-        kernel_output(mask[i * b:(i + 1) * b], x, ei_np, arch, q)
+        wl.oracle_eval(om, mask[i * b:(i + 1) * b])
         dt = time.perf_counter() - t0
         if i >= args.warmup:
             times.append(dt)
@@ -171,8 +265,8 @@ def run_reference(args, rank):
         "impl": "reference", "metric": "coalition evals/s", "value": value, "unit": "coalition evals/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": config_dict(args, n, e, h, c),
-        "masked_gteps": value * 2 * e / 1e9,
+        "config": config_dict(args, wl),
+        "masked_gteps": value * 2 * wl.e / 1e9,
         "cpu_baseline": {"value": value, "unit": "coalition evals/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": "%d coalitions per step of the full %s workload (oracle port of the reference's "
                                    "block-diagonal path, torch CPU)" % (b, args.workload)},
@@ -181,9 +275,9 @@ def run_reference(args, rank):
     emit(line)
 
 
-def config_dict(args, n, e, h, c):
-    return {"workload": args.workload, "nodes": n, "edges": e, "model": "2xGCNConv(%d)+Linear(%d,1)" % (h, h),
-            "communities": c, "coalitions_per_gpu_per_step": args.coalitions_per_gpu, "mode": "full (every conv layer "
+def config_dict(args, wl):
+    return {"workload": args.workload, "nodes": wl.n, "edges": wl.e, "model": wl.model_name, "queries": len(wl.queries),
+            "communities": wl.c, "coalitions_per_gpu_per_step": args.coalitions_per_gpu, "mode": "full (every conv layer "
             "over the whole-graph computational graph; per coalition only rows of active nodes are materialised, "
             "inactive rows are coalition invariant)", "l2": "inputs larger than L2 (activation tiles of "
             "16 GiB vs 126 MB L2)", "precision": getattr(args, "precision", "fp32") + (
@@ -233,8 +327,6 @@ def main():
     import torch.distributed as dist
 
     from bikg_graph_explainability_public_b200 import _lib
-    from bikg_graph_explainability_public_b200.engine import GraphSpec, MaskedForward
-    from bikg_graph_explainability_public_b200.lowering import lower
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -242,17 +334,17 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 
-    n, e, f, h, c, x, ei, com_of = make_graph(args.workload)
-    arch = make_model(f, h)
-    q = 17
-    eng = MaskedForward(GraphSpec(x.to(dev), ei.to(dev), [0, n]), lower(arch), [q], prune=False, precision=args.precision)
+    wl = Workload(args.workload)
+    n, e, h, c, com_of = wl.n, wl.e, wl.h, wl.c, wl.com_of
+    arch, eng = wl.engine(dev, args.precision)
+    nq = len(wl.queries)
     s_local = args.coalitions_per_gpu
     w = -(-s_local // 32)
     mask_host = make_masks(s_local, n, c, com_of, 1000 + rank).pin_memory()
     mask_dev = torch.empty_like(mask_host, device=dev)
     act = torch.zeros((n, w), dtype=torch.int32, device=dev)
     pop = torch.zeros(s_local, dtype=torch.int32, device=dev)
-    y_all = torch.empty((world * s_local, 1), dtype=torch.float32, device=dev)
+    y_all = torch.empty((world * s_local, nq), dtype=torch.float32, device=dev)
 
     def pack():
         _lib.check(lib.xpgnn_pack_mask(mask_dev.data_ptr(), s_local, n, act.data_ptr(), w, pop.data_ptr(),
@@ -314,7 +406,7 @@ def main():
     e2e_total = float(e2e_s.item())
 
     if rank == 0:
-        evals = world * s_local * args.steps
+        evals = world * s_local * args.steps * nq  # coalition rows x queries
         value = evals / (ms_total / 1e3)
         visits = eng.edge_visits_per_coalition  # kept edges x conv layers
         # algorithmic bytes of one coalition-layer: col idx + rowptr + bits + read Z once + write
@@ -349,13 +441,16 @@ def main():
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
-            "config": config_dict(args, n, e, h, c),
-            "masked_gteps": value * visits / 1e9,
+            "config": config_dict(args, wl),
+            "coalition_rows_per_s": value / nq,
+            "masked_gteps": value / nq * visits / 1e9,
             "e2e": {"value": evals / e2e_total, "unit": "coalition evals/s",
                     "h2d_bytes_per_step": int(mask_host.numel()), "d2h_bytes_per_step": int(y_host.numel() * 4)},
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
-            "roofline": {"bound": "hbm", "kernel": "cspmm_kernel (%s)" % dom,
+            "roofline": {"bound": "hbm", "kernel": "%s (%s)" % (
+                ("cspmm_kernel" if dom == "spmm_tile_l1" else "l0_rows_kernel") if kern["compaction"]["launches"]
+                else "spmm_masked_kernel", dom),
                          "achieved": roof.get(dom, {}).get("achieved_gbs"), "peak": peak, "unit": "GB/s",
                          "frac": roof.get(dom, {}).get("frac"), "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
@@ -365,25 +460,23 @@ def main():
             "kernel_share_of_step": share,
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(args, n, f, h, x, ei, arch, mask_host, q, y_host)
+            line["cpu_baseline"] = cpu_baseline(args, wl, arch, mask_host, y_host)
         emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_baseline(args, n, f, h, x, ei, arch, mask_host, q, y_gpu):
+def cpu_baseline(args, wl, arch, mask_host, y_gpu):
     """Oracle port on the host cores over a bounded sample of the same workload; also the parity check."""
-    from oracle.xpgnn_oracle import kernel_output
-
     torch.set_num_threads(os.cpu_count())
     b = args.cpu_coalitions
     m = mask_host[:b].bool().numpy()
-    om = oracle_model(arch, f, h)
+    om = wl.oracle_model(arch)
     t0 = time.perf_counter()
-    _, y_ref = kernel_output(m, x, ei.numpy(), om, q)
+    y_ref = wl.oracle_eval(om, m)
     dt = time.perf_counter() - t0
-    y_ref = y_ref.numpy().reshape(-1)
-    rel = float(np.max(np.abs(y_gpu.numpy().reshape(-1)[:b] - y_ref) / np.maximum(np.abs(y_ref), 1e-6)))
+    y0 = y_gpu.numpy().reshape(len(mask_host), -1)[:b, 0]
+    rel = float(np.max(np.abs(y0 - y_ref) / np.maximum(np.abs(y_ref), 1e-6)))
     return {"value": b / dt, "unit": "coalition evals/s", "cores": torch.get_num_threads(), "kind": "port",
             "sample": "%d coalitions of the full %s workload in one batch (%.1f s of CPU work)" % (b, args.workload, dt),
             "gpu_vs_oracle_max_rel_err": rel}
