@@ -33,16 +33,29 @@ constexpr unsigned long long kEdgeMask = (1ull << kKeyShift) - 1ull;
 constexpr int kMaxConvIso = 8;
 constexpr int kMaxHeadC = 8;
 
+// Dynamic row scheduling for the row-per-warp kernels: a warp takes kRowGrab consecutive rows at a time from a
+// global counter.  (A static stride is badly unbalanced on power-law graphs: with R-MAT ids the in-degree is a
+// function of the id's bit pattern, and a stride that is a multiple of 64 hands some CTAs rows ~1000x heavier.)
+constexpr int kRowGrab = 4;
+__device__ __forceinline__ int grab_rows(int32_t* counter, int lane) {
+  int base = 0;
+  if (lane == 0) base = atomicAdd(counter, kRowGrab);
+  return __shfl_sync(0xffffffffu, base, 0);
+}
+
 // ------------------------------------------------------------------------------------------
 // pass 1: edge-activity words of the coalition word + packed per-(coalition, node) counts
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) compact_degree_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                                                              const uint32_t* __restrict__ act, int W, int w, int b0, int nb, int N,
                                                              uint32_t* __restrict__ ebits, unsigned long long* __restrict__ keys,
-                                                             float* __restrict__ scale, int kind) {
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  for (int v = blockIdx.x * wpb + wib; v < N; v += gridDim.x * wpb) {
+                                                             float* __restrict__ scale, int kind, int32_t* __restrict__ counter,
+                                                             int long_threshold) {
+  const int lane = threadIdx.x & 31;
+  for (int vb = grab_rows(counter, lane); vb < N; vb = grab_rows(counter, lane))
+  for (int v = vb; v < min(N, vb + kRowGrab); ++v) {
     const int e0 = rowptr[v], e1 = rowptr[v + 1];
+    if (long_threshold > 0 && e1 - e0 > long_threshold) continue;  // hub row: compact_degree_long_kernel
     const uint32_t av = act[(int64_t)v * W + w];
     int cnt = 0;
     for (int base = e0; base < e1; base += 32) {
@@ -62,6 +75,43 @@ __global__ void __launch_bounds__(256) compact_degree_kernel(const int32_t* __re
   }
 }
 
+// hub rows of pass 1: one CTA per row, the warps take the 32-edge batches round-robin, counts summed through shared memory
+__global__ void __launch_bounds__(256) compact_degree_long_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                                  const uint32_t* __restrict__ act, int W, int w, int b0, int nb, int N,
+                                                                  uint32_t* __restrict__ ebits, unsigned long long* __restrict__ keys,
+                                                                  float* __restrict__ scale, int kind, const int32_t* __restrict__ long_rows) {
+  __shared__ int s_cnt[8][32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int v = long_rows[blockIdx.x];
+  const int e0 = rowptr[v], e1 = rowptr[v + 1];
+  const uint32_t av = act[(int64_t)v * W + w];
+  int cnt = 0;
+  for (int base = e0 + 32 * wib; base < e1; base += 256) {
+    const int e = base + lane;
+    uint32_t bits = 0;
+    if (e < e1) {
+      bits = act[(int64_t)col[e] * W + w] & av;
+      ebits[e] = bits;
+    }
+    const int n = min(32, e1 - base);
+    for (int j = 0; j < n; ++j) cnt += (__shfl_sync(0xffffffffu, bits, j) >> lane) & 1u;
+  }
+  s_cnt[wib][lane] = cnt;
+  __syncthreads();
+  if (wib != 0) return;
+  for (int w8 = 1; w8 < 8; ++w8) cnt += s_cnt[w8][lane];
+  if (scale) scale[(int64_t)v * 32 + lane] = kind == XPGNN_CONV_GCN ? gcn_dinv((uint32_t)cnt) : 1.0f / (float)max(cnt, 1);
+  const int t = lane - b0;
+  if (t >= 0 && t < nb) keys[(int64_t)t * N + v] = ((av >> lane) & 1u) ? ((1ull << kKeyShift) | (unsigned long long)cnt) : 0ull;
+}
+
+// destination rows with more than `threshold` in-edges (a property of the graph: found once per forward call)
+__global__ void __launch_bounds__(256) find_long_rows_kernel(const int32_t* __restrict__ rowptr, int N, int threshold,
+                                                             int32_t* __restrict__ list, int32_t* __restrict__ count) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < N && rowptr[v + 1] - rowptr[v] > threshold) list[atomicAdd(count, 1)] = v;
+}
+
 // pass 2 (after the exclusive scan of the keys): per-coalition list of active rows, compact in-edge
 // offsets, per-source GCN weight of layer 0, per-slot totals
 __global__ void __launch_bounds__(256) compact_finalize_kernel(const unsigned long long* __restrict__ keys,
@@ -69,7 +119,8 @@ __global__ void __launch_bounds__(256) compact_finalize_kernel(const unsigned lo
                                                                int32_t* __restrict__ act_list, uint32_t* __restrict__ rowptr_c,
                                                                float* __restrict__ wgt, int2* __restrict__ slot_info,
                                                                long long* __restrict__ slot_base, int32_t* __restrict__ rows_packed,
-                                                               float* __restrict__ rs_packed) {
+                                                               float* __restrict__ rs_packed, int long_cnt, int32_t* __restrict__ long_list,
+                                                               int32_t* __restrict__ n_long_list) {
   const int t = blockIdx.y;
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   // first 128-row tile of this slot in the concatenated, per-slot padded tile table
@@ -90,6 +141,8 @@ __global__ void __launch_bounds__(256) compact_finalize_kernel(const unsigned lo
     rowptr_c[(int64_t)t * (N + 1) + i] = (uint32_t)((S & kEdgeMask) - (B & kEdgeMask));
     rows_packed[(int64_t)s_tile0 * 128 + i] = (int32_t)(((uint32_t)t << kPackShift) | (uint32_t)v);
     rs_packed[(int64_t)s_tile0 * 128 + i] = gcn_dinv((uint32_t)(K & kEdgeMask));
+    if (long_cnt > 0 && (K & kEdgeMask) > (unsigned long long)long_cnt)  // hub row of this coalition: cspmm_long_kernel
+      long_list[atomicAdd(n_long_list, 1)] = (int32_t)(((uint32_t)t << kPackShift) | (uint32_t)i);
   }
   if (wgt) wgt[g] = gcn_dinv((uint32_t)(K & kEdgeMask));
   if (v == N - 1) {
@@ -132,15 +185,17 @@ __global__ void __launch_bounds__(256) compact_tilemap_kernel(const int2* __rest
 __global__ void __launch_bounds__(256) compact_edges_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                                                             const uint32_t* __restrict__ ebits, const uint32_t* __restrict__ act, int W,
                                                             int w, int b0, int nb, int N, const unsigned long long* __restrict__ scanned,
-                                                            int32_t* __restrict__ ccol) {
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+                                                            int32_t* __restrict__ ccol, int32_t* __restrict__ counter, int long_threshold) {
+  const int lane = threadIdx.x & 31;
   const uint32_t tile_mask = nb == 32 ? 0xffffffffu : ((1u << nb) - 1u);
   const uint32_t lt = (1u << lane) - 1u;
-  for (int v = blockIdx.x * wpb + wib; v < N; v += gridDim.x * wpb) {
+  for (int vb = grab_rows(counter, lane); vb < N; vb = grab_rows(counter, lane))
+  for (int v = vb; v < min(N, vb + kRowGrab); ++v) {
     const uint32_t av = (act[(int64_t)v * W + w] >> b0) & tile_mask;
     if (!av) continue;
     const int e0 = rowptr[v], e1 = rowptr[v + 1];
     if (e0 == e1) continue;
+    if (long_threshold > 0 && e1 - e0 > long_threshold) continue;  // hub row: compact_edges_long_kernel
     unsigned long long base = 0;  // lane t: write cursor of slot t (offset into the concatenated lists)
     if ((av >> lane) & 1u) base = scanned[(int64_t)lane * N + v] & kEdgeMask;
     for (int b = e0; b < e1; b += 32) {
@@ -185,7 +240,64 @@ struct L0RowsArgs {
   float* out;                // chunk-major (cw = 32) activations of the tile
   int64_t out_s_stride, out_chunk_stride;
   int kind, act_fn, prescale;
+  const int32_t* long_rows;  // rows with more than long_threshold in-edges (hub rows): one CTA each in the LONG variant
+  int long_threshold;        // 0: no splitting
+  int32_t* counter;          // row counter of the dynamic schedule (zero at launch)
 };
+
+constexpr int kLongRow = 1024;    // in-edges above which a destination row is processed by a whole CTA
+constexpr int kLongCompact = 256; // active in-edges above which a compact row is processed by a whole CTA (SpMM)
+
+// hub rows of pass 3: one CTA per row.  The warps take contiguous slices of the row's in-edges; a first sweep counts the
+// active edges of every slot per slice, the exclusive sum over the slices gives each warp its write cursors, a second
+// sweep writes the sources (CSR order kept).
+__global__ void __launch_bounds__(256) compact_edges_long_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                                 const uint32_t* __restrict__ ebits, const uint32_t* __restrict__ act, int W,
+                                                                 int w, int b0, int nb, int N, const unsigned long long* __restrict__ scanned,
+                                                                 int32_t* __restrict__ ccol, const int32_t* __restrict__ long_rows) {
+  __shared__ int s_cnt[8][32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t tile_mask = nb == 32 ? 0xffffffffu : ((1u << nb) - 1u);
+  const uint32_t lt = (1u << lane) - 1u;
+  const int v = long_rows[blockIdx.x];
+  const uint32_t av = (act[(int64_t)v * W + w] >> b0) & tile_mask;
+  if (!av) return;
+  const int e0 = rowptr[v], e1 = rowptr[v + 1];
+  const int nbatch = (e1 - e0 + 31) >> 5;
+  const int bs = e0 + 32 * ((wib * nbatch) >> 3), be = min(e1, e0 + 32 * (((wib + 1) * nbatch) >> 3));
+  int cnt = 0;  // lane t: active edges of slot t in this warp's slice
+  for (int b = bs; b < be; b += 32) {
+    const int e = b + lane;
+    const uint32_t bits = e < be ? (__ldg(ebits + e) >> b0) & tile_mask : 0u;
+    const int n = min(32, be - b);
+    for (int j = 0; j < n; ++j) cnt += (__shfl_sync(0xffffffffu, bits, j) >> lane) & 1u;
+  }
+  s_cnt[wib][lane] = cnt;
+  __syncthreads();
+  unsigned long long base = 0;
+  if ((av >> lane) & 1u) {
+    base = scanned[(int64_t)lane * N + v] & kEdgeMask;
+    for (int w8 = 0; w8 < wib; ++w8) base += s_cnt[w8][lane];
+  }
+  for (int b = bs; b < be; b += 32) {
+    const int e = b + lane;
+    int u = -1;
+    uint32_t bits = 0;
+    if (e < be) {
+      u = __ldg(col + e);
+      bits = (__ldg(ebits + e) >> b0) & tile_mask;
+    }
+    uint32_t rem = __reduce_or_sync(0xffffffffu, bits);
+    while (rem) {
+      const int t = __ffs(rem) - 1;
+      rem &= rem - 1;
+      const uint32_t m = __ballot_sync(0xffffffffu, (bits >> t) & 1u);
+      const unsigned long long bt = __shfl_sync(0xffffffffu, base, t);
+      if ((bits >> t) & 1u) ccol[bt + __popc(m & lt)] = u;
+      if (lane == t) base += __popc(m);
+    }
+  }
+}
 
 constexpr int kL0WStride = 36;  // floats per staged weight row (32 + pad: 16-byte aligned, 4-way instead of 32-way store conflicts)
 constexpr int kL0SmemBytes = 8 * 32 * kL0WStride * 4 + 8 * 32 * 64 * 4 + 8 * 32 * 4;
@@ -223,7 +335,9 @@ __device__ __forceinline__ void l0_fma(const float* __restrict__ w_rows, const f
   }
 }
 
-template <bool SIGMOID>
+// LONG: one CTA per hub row -- the 8 warps take contiguous slices of the row's in-edges, the partial accumulators
+// are summed through shared memory in a fixed order (deterministic) and warp 0 runs the epilogue.
+template <bool SIGMOID, bool LONG>
 __global__ void __launch_bounds__(256, 2) l0_rows_kernel(const L0RowsArgs a) {
   extern __shared__ __align__(16) uint8_t l0_smem[];
   float(*s_w)[32][kL0WStride] = reinterpret_cast<float(*)[32][kL0WStride]>(l0_smem);
@@ -234,19 +348,27 @@ __global__ void __launch_bounds__(256, 2) l0_rows_kernel(const L0RowsArgs a) {
   const bool gcn = a.kind == XPGNN_CONV_GCN;
   const int ncb = a.h0 / 64;
   const float lower = a.act_fn == XPGNN_ACT_RELU ? 0.0f : -INFINITY;
-  for (int v = blockIdx.x * 8 + wib; v < a.N; v += gridDim.x * 8) {
+  for (int vb = LONG ? 0 : grab_rows(a.counter, lane); vb < a.N; vb = LONG ? a.N : grab_rows(a.counter, lane))
+  for (int v = LONG ? a.long_rows[blockIdx.x] : vb; v < (LONG ? a.N : min(a.N, vb + kRowGrab)); v += LONG ? a.N : 1) {
     const uint32_t av = a.act[(int64_t)v * a.W + a.w] & live;
-    if (!av) continue;
+    if (!av) continue;  // LONG: the same row for the whole CTA, so every warp leaves together
     const int n_slots = __popc(av), nq = (n_slots + 3) >> 2;
     const int e0 = a.rowptr[v], e1 = a.rowptr[v + 1];
-    const bool short_row = e1 - e0 <= 32;
+    if (!LONG && a.long_threshold > 0 && e1 - e0 > a.long_threshold) continue;  // hub row: left to the LONG launch
+    const bool short_row = !LONG && e1 - e0 <= 32;
     const float sc_v = a.scale[(int64_t)v * 32 + lane];
+    int bs = e0, be = e1;  // this warp's slice of the in-edges
+    if (LONG) {
+      const int nbatch = (e1 - e0 + 31) >> 5;
+      bs = e0 + 32 * ((wib * nbatch) >> 3);
+      be = min(e1, e0 + 32 * (((wib + 1) * nbatch) >> 3));
+    }
     for (int cb = 0; cb < ncb; ++cb) {
       float2 acc[32];
 #pragma unroll
       for (int k = 0; k < 32; ++k) acc[k] = make_float2(0.f, 0.f);
-      for (int base = e0; base < e1; base += 32) {
-        const int n = min(32, e1 - base);
+      for (int base = bs; base < be; base += 32) {
+        const int n = min(32, be - base);
         __syncwarp();
         if (cb == 0 || !short_row) {  // weights of the batch (kept across column blocks for short rows)
           if (lane < n) {
@@ -292,6 +414,24 @@ __global__ void __launch_bounds__(256, 2) l0_rows_kernel(const L0RowsArgs a) {
           case 7: l0_fma<7>(wr, zr, n, lane, acc); break;
           default: l0_fma<8>(wr, zr, n, lane, acc); break;
         }
+      }
+      if (LONG) {  // sum the 8 partial accumulators (fixed order) into warp 0
+        float2* red = reinterpret_cast<float2*>(&s_z[0][0][0]);
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 32; ++k) red[(wib * 32 + k) * 32 + lane] = acc[k];
+        __syncthreads();
+        if (wib == 0) {
+          for (int w8 = 1; w8 < 8; ++w8) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+              const float2 p = red[(w8 * 32 + k) * 32 + lane];
+              acc[k].x += p.x; acc[k].y += p.y;
+            }
+          }
+        }
+        __syncthreads();
+        if (wib != 0) continue;
       }
       // ---- epilogue of the column block: position k of the accumulators is the k-th active slot ----
       const float* zs = a.z + (int64_t)v * a.h0 + cb * 64 + lane * 2;
@@ -380,10 +520,40 @@ struct CspmmArgs {
   int64_t add_chunk_stride;
   const float* bias;          // per-column addend or NULL
   int32_t* counter;           // work counter (zeroed per launch); NULL: static round-robin
+  int long_cnt;               // compact rows with more active in-edges are left to cspmm_long_kernel (0: none)
+  const int32_t* long_list;   // entries slot << 26 | compact row, written by compact_finalize_kernel
+  const int32_t* n_long_list;
   int l2_stream, l2_gather;   // eviction priority of the streamed / gathered accesses (l2_policy kinds)
   float* out;
   int64_t out_s_stride, out_chunk_stride;
 };
+
+// finishes one row piece (CW / 4 lanes x float4): normalisation, self term, addend, activation, pre-scale, store
+template <int CW>
+__device__ __forceinline__ void cspmm_epilogue(const CspmmArgs& a, uint32_t cnt, const float4& acc, const float* in_c, float* out_c,
+                                               const float* add_c, const float4& bias, int v, uint64_t pol_s, uint64_t pol_g) {
+  float4 o;
+  float dinv = 1.0f;
+  if (a.kind == XPGNN_CONV_GCN) {
+    dinv = gcn_dinv(cnt);
+    const float4 self = ld_hint4(in_c + (int64_t)v * CW, pol_g);
+    const float sw = a.layer0 ? dinv : 1.0f;  // layers >= 1 gather operands already scaled by deg^-1/2
+    o.x = dinv * fmaf(sw, self.x, acc.x); o.y = dinv * fmaf(sw, self.y, acc.y);
+    o.z = dinv * fmaf(sw, self.z, acc.z); o.w = dinv * fmaf(sw, self.w, acc.w);
+  } else {
+    const float inv = 1.0f / (float)max(cnt, 1u);
+    o.x = acc.x * inv; o.y = acc.y * inv; o.z = acc.z * inv; o.w = acc.w * inv;
+  }
+  o.x += bias.x; o.y += bias.y; o.z += bias.z; o.w += bias.w;
+  if (add_c) {
+    const float4 ad = ld_hint4(add_c + (int64_t)v * CW, pol_s);
+    o.x += ad.x; o.y += ad.y; o.z += ad.z; o.w += ad.w;
+  }
+  o.x = apply_act(o.x, a.act_fn); o.y = apply_act(o.y, a.act_fn);
+  o.z = apply_act(o.z, a.act_fn); o.w = apply_act(o.w, a.act_fn);
+  if (a.prescale) { o.x *= dinv; o.y *= dinv; o.z *= dinv; o.w *= dinv; }
+  st_hint4(out_c + (int64_t)v * CW, o, pol_s);
+}
 
 template <int CW, bool WEIGHTED, int OCC>
 __global__ void __launch_bounds__(256, OCC) cspmm_kernel(const CspmmArgs a) {
@@ -433,6 +603,9 @@ __global__ void __launch_bounds__(256, OCC) cspmm_kernel(const CspmmArgs a) {
         e0 = ld_hint(rp + i, pol_s);
         cnt = ld_hint(rp + i + 1, pol_s) - e0;
       }
+      const bool is_long = a.long_cnt > 0 && cnt > (uint32_t)a.long_cnt;  // left to cspmm_long_kernel
+      const uint32_t cnt_all = cnt;
+      if (is_long) cnt = 0;
       const uint32_t maxcnt = __reduce_max_sync(0xffffffffu, cnt);
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       for (uint32_t base = 0; base < maxcnt; base += G) {
@@ -453,31 +626,66 @@ __global__ void __launch_bounds__(256, OCC) cspmm_kernel(const CspmmArgs a) {
           }
         }
       }
-      if (valid) {
-        float4 o;
-        float dinv = 1.0f;
-        if (a.kind == XPGNN_CONV_GCN) {
-          dinv = gcn_dinv(cnt);
-          const float4 self = ld_hint4(in_c + (int64_t)v * CW, pol_g);
-          const float sw = a.layer0 ? dinv : 1.0f;  // layers >= 1 gather operands already scaled by deg^-1/2
-          o.x = dinv * fmaf(sw, self.x, acc.x); o.y = dinv * fmaf(sw, self.y, acc.y);
-          o.z = dinv * fmaf(sw, self.z, acc.z); o.w = dinv * fmaf(sw, self.w, acc.w);
-        } else {
-          const float inv = 1.0f / (float)max(cnt, 1u);
-          o.x = acc.x * inv; o.y = acc.y * inv; o.z = acc.z * inv; o.w = acc.w * inv;
-        }
-        o.x += bias.x; o.y += bias.y; o.z += bias.z; o.w += bias.w;
-        if (add_c) {
-          const float4 ad = ld_hint4(add_c + (int64_t)v * CW, pol_s);
-          o.x += ad.x; o.y += ad.y; o.z += ad.z; o.w += ad.w;
-        }
-        o.x = apply_act(o.x, a.act_fn); o.y = apply_act(o.y, a.act_fn);
-        o.z = apply_act(o.z, a.act_fn); o.w = apply_act(o.w, a.act_fn);
-        if (a.prescale) { o.x *= dinv; o.y *= dinv; o.z *= dinv; o.w *= dinv; }
-        st_hint4(out_c + (int64_t)v * CW, o, pol_s);
-      }
+      if (valid && !is_long) cspmm_epilogue<CW>(a, cnt_all, acc, in_c, out_c, add_c, bias, v, pol_s, pol_g);
     }
     if (!a.counter) idx += gridDim.x;
+  }
+}
+
+// Long compact rows (hub rows of power-law graphs): one CTA per (row, chunk).  The 32 row groups of the CTA take
+// contiguous slices of the row's active in-edges; the partial sums are added in a fixed order through shared memory.
+template <int CW, bool WEIGHTED>
+__global__ void __launch_bounds__(256) cspmm_long_kernel(const CspmmArgs a) {
+  constexpr int G = CW / 4, NG = 256 / G;
+  __shared__ float4 s_red[256];
+  const int lane = threadIdx.x & 31, sub = threadIdx.x % G, g = threadIdx.x / G, grp = lane / G;
+  const uint64_t pol_s = l2_policy(a.l2_stream), pol_g = l2_policy(a.l2_gather);
+  const int total = *a.n_long_list * a.n_chunks;
+  for (int idx = blockIdx.x; idx < total; idx += gridDim.x) {
+    const int32_t ent = a.long_list[idx / a.n_chunks];
+    const int c = idx % a.n_chunks, t = (int)((uint32_t)ent >> kPackShift), i = ent & ((1 << kPackShift) - 1);
+    const uint32_t* rp = a.rowptr_c + (int64_t)t * (a.N + 1);
+    const int v = a.act_list[(int64_t)t * a.N + i];
+    const uint32_t e0 = rp[i], cnt = rp[i + 1] - e0;
+    const int32_t* cc = a.ccol + a.slot_base[t] + e0;
+    const float* in_c = a.in + (int64_t)t * a.in_s_stride + (int64_t)c * a.in_chunk_stride + sub * 4;
+    const float* wg = WEIGHTED ? a.wgt + (int64_t)t * a.N : nullptr;
+    float* out_c = a.out + (int64_t)t * a.out_s_stride + (int64_t)c * a.out_chunk_stride + sub * 4;
+    const float* add_c = a.addend ? a.addend + (int64_t)c * a.add_chunk_stride + sub * 4 : nullptr;
+    float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.bias) bias = __ldg(reinterpret_cast<const float4*>(a.bias + c * CW + sub * 4));
+    const uint32_t nbt = (cnt + G - 1) / G;  // batches of G edges, split evenly over the NG groups
+    const uint32_t bs = (uint32_t)(((uint64_t)g * nbt) / NG) * G, be = min(cnt, (uint32_t)(((uint64_t)(g + 1) * nbt) / NG) * G);
+    const uint32_t span = __reduce_max_sync(0xffffffffu, be > bs ? be - bs : 0u);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (uint32_t off = 0; off < span; off += G) {
+      int my = -1;
+      float myw = 0.f;
+      if (bs + off + sub < be) {
+        my = ld_hint(cc + bs + off + sub, pol_s);
+        if (WEIGHTED) myw = __ldg(wg + my);
+      }
+#pragma unroll
+      for (int j = 0; j < G; ++j) {
+        const int u = __shfl_sync(0xffffffffu, my, grp * G + j);
+        const float wj = WEIGHTED ? __shfl_sync(0xffffffffu, myw, grp * G + j) : 1.0f;
+        if (u >= 0) {
+          const float4 x = ld_hint4(in_c + (int64_t)u * CW, pol_g);
+          acc.x = fmaf(wj, x.x, acc.x); acc.y = fmaf(wj, x.y, acc.y);
+          acc.z = fmaf(wj, x.z, acc.z); acc.w = fmaf(wj, x.w, acc.w);
+        }
+      }
+    }
+    __syncthreads();  // the previous item's reduction has been read
+    s_red[threadIdx.x] = acc;
+    __syncthreads();
+    if (g == 0) {
+      for (int k = 1; k < NG; ++k) {
+        const float4 p = s_red[k * G + sub];
+        acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+      }
+      cspmm_epilogue<CW>(a, cnt, acc, in_c, out_c, add_c, bias, v, pol_s, pol_g);
+    }
   }
 }
 
@@ -592,6 +800,8 @@ struct CLayout {
   int2* slot_info;
   long long* slot_base;
   int32_t *slot_tile_start, *n_tiles, *counters;
+  int32_t *long_rows, *n_long;
+  int32_t *long_list, *n_long_list;
   int32_t* rows_packed;
   float* rs_packed;
   int32_t* ccol;
@@ -624,6 +834,10 @@ static CLayout compact_carve(const xpgnn_plan_t* p, void* ws, int64_t cap, int t
   c.slot_tile_start = b.take<int32_t>(33);
   c.n_tiles = b.take<int32_t>(1);
   c.counters = b.take<int32_t>(16);
+  c.long_rows = b.take<int32_t>(E / kLongRow + 1);
+  c.n_long = b.take<int32_t>(1);
+  c.long_list = b.take<int32_t>((int64_t)tile * (E / kLongCompact + 1));
+  c.n_long_list = b.take<int32_t>(1);
   c.rows_packed = b.take<int32_t>((int64_t)tile * ceil_div(N, 128) * 128);
   c.rs_packed = b.take<float>((int64_t)tile * ceil_div(N, 128) * 128);
   c.ccol = b.take<int32_t>((int64_t)tile * E);
@@ -652,6 +866,11 @@ static int launch_cspmm(const CspmmArgs& a, int cw, cudaStream_t st) {
   const int grid = kNumSMs * std::max(per_sm, 1);
   ProfScope ps(a.layer0 ? PROF_SPMM_INVARIANT : PROF_SPMM_TILE, st);
   XP_LAUNCH(k, grid, 256, 0, st, a);
+  if (a.long_cnt > 0) {
+    void (*kl)(const CspmmArgs) = cw == 32 ? (a.wgt ? cspmm_long_kernel<32, true> : cspmm_long_kernel<32, false>)
+                                           : (a.wgt ? cspmm_long_kernel<16, true> : cspmm_long_kernel<16, false>);
+    XP_LAUNCH(kl, kNumSMs * 8, 256, 0, st, a);
+  }
   return 0;
 }
 
@@ -696,6 +915,14 @@ int forward_compact(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32
   const int l2_gather = getenv("XPGNN_L2_GATHER") ? atoi(getenv("XPGNN_L2_GATHER")) : 0;
   const bool dyn_sched = !(getenv("XPGNN_SCHED") && std::string(getenv("XPGNN_SCHED")) == "static");
   XP_CHECK(cudaMemsetAsync(lay.keys + (int64_t)tile * N, 0, sizeof(unsigned long long), st));
+  // hub rows get CTA-per-row variants of the row-per-warp kernels
+  int n_long = 0;
+  XP_CHECK(cudaMemsetAsync(lay.counters, 0, 16 * sizeof(int32_t), st));  // later zeroed per tile by compact_tilemap_kernel
+  XP_CHECK(cudaMemsetAsync(lay.n_long, 0, sizeof(int32_t), st));
+  XP_LAUNCH(find_long_rows_kernel, (int)ceil_div(N, 256), 256, 0, st, R0.rowptr, N, kLongRow, lay.long_rows, lay.n_long);
+  XP_CHECK(cudaMemcpyAsync(&n_long, lay.n_long, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  XP_CHECK(cudaStreamSynchronize(st));
+  if (getenv("XPGNN_LONG") && std::string(getenv("XPGNN_LONG")) == "0") n_long = 0;
 
   const int w_first = s0 / 32, w_last = (s0 + n_s - 1) / 32;
   const int grid_rows = (int)std::min<int64_t>(std::max<int64_t>(ceil_div(N, 8), 1), (int64_t)kNumSMs * 8);
@@ -707,19 +934,27 @@ int forward_compact(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32
       {
         ProfScope ps(PROF_SCALE, st);
         XP_LAUNCH(compact_degree_kernel, grid_rows, 256, 0, st, R0.rowptr, R0.col, act, W, w, b0, nb, N, lay.ebits, lay.keys,
-                  l0_rows ? lay.scale : nullptr, kind);
+                  l0_rows ? lay.scale : nullptr, kind, lay.counters + 15, n_long > 0 ? kLongRow : 0);
+        if (n_long > 0)
+          XP_LAUNCH(compact_degree_long_kernel, n_long, 256, 0, st, R0.rowptr, R0.col, act, W, w, b0, nb, N, lay.ebits, lay.keys,
+                    l0_rows ? lay.scale : nullptr, kind, lay.long_rows);
       }
       {
         ProfScope ps(PROF_COMPACT, st);
         if (nb < tile) XP_CHECK(cudaMemsetAsync(lay.keys + (int64_t)nb * N, 0, sizeof(unsigned long long), st));
+        XP_CHECK(cudaMemsetAsync(lay.n_long_list, 0, sizeof(int32_t), st));
         size_t tmp = lay.cub_bytes;
         XP_CHECK(cub::DeviceScan::ExclusiveSum(lay.cub_tmp, tmp, lay.keys, lay.scanned, (int64_t)nb * N + 1, st));
         g_launches.fetch_add(1, std::memory_order_relaxed);
         XP_LAUNCH(compact_finalize_kernel, dim3((unsigned)ceil_div(N, 256), (unsigned)nb), 256, 0, st, lay.keys, lay.scanned, N,
                   lay.act_list, lay.rowptr_c, (kind == XPGNN_CONV_GCN && !l0_rows) ? lay.wgt : nullptr, lay.slot_info, lay.slot_base,
-                  lay.rows_packed, lay.rs_packed);
+                  lay.rows_packed, lay.rs_packed, n_long > 0 ? kLongCompact : 0, lay.long_list, lay.n_long_list);
         XP_LAUNCH(compact_tilemap_kernel, 1, 256, 0, st, lay.slot_info, nb, lay.slot_tile_start, lay.n_tiles, NL, stats, lay.counters);
-        XP_LAUNCH(compact_edges_kernel, grid_rows, 256, 0, st, R0.rowptr, R0.col, lay.ebits, act, W, w, b0, nb, N, lay.scanned, lay.ccol);
+        XP_LAUNCH(compact_edges_kernel, grid_rows, 256, 0, st, R0.rowptr, R0.col, lay.ebits, act, W, w, b0, nb, N, lay.scanned, lay.ccol,
+                  lay.counters + 14, n_long > 0 ? kLongRow : 0);
+        if (n_long > 0)
+          XP_LAUNCH(compact_edges_long_kernel, n_long, 256, 0, st, R0.rowptr, R0.col, lay.ebits, act, W, w, b0, nb, N, lay.scanned,
+                    lay.ccol, lay.long_rows);
       }
       float* cur = lay.hbuf[0];
       float* nxt = lay.hbuf[1];
@@ -734,6 +969,7 @@ int forward_compact(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32
         s.in_chunk_stride = cstride; s.out_s_stride = hstride; s.out_chunk_stride = cstride;
         s.counter = dyn_sched ? lay.counters + l : nullptr;
         s.l2_stream = l2_stream; s.l2_gather = l2_gather;
+        s.long_cnt = n_long > 0 ? kLongCompact : 0; s.long_list = lay.long_list; s.n_long_list = lay.n_long_list;
         if (l == 0 && l0_rows) {
           L0RowsArgs r{};
           r.rowptr = R.rowptr; r.col = R.col; r.ebits = lay.ebits; r.act = act; r.W = W; r.w = w; r.b0 = b0; r.nb = nb; r.N = N;
@@ -743,10 +979,16 @@ int forward_compact(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32
           r.out = cur; r.out_s_stride = hstride; r.out_chunk_stride = cstride;
           r.kind = kind; r.act_fn = L.act; r.prescale = next_gcn;
           ProfScope ps(PROF_SPMM_INVARIANT, st);
-          const int grid = (int)std::min<int64_t>(ceil_div(N, 8), (int64_t)kNumSMs * 2);
-          void (*k0)(const L0RowsArgs) = L.act == XPGNN_ACT_SIGMOID ? l0_rows_kernel<true> : l0_rows_kernel<false>;
+          const int grid = (int)std::min<int64_t>(ceil_div(N, 8 * kRowGrab), (int64_t)kNumSMs * 2);
+          r.long_rows = lay.long_rows; r.long_threshold = n_long > 0 ? kLongRow : 0; r.counter = lay.counters + 13;
+          void (*k0)(const L0RowsArgs) = L.act == XPGNN_ACT_SIGMOID ? l0_rows_kernel<true, false> : l0_rows_kernel<false, false>;
           XP_CHECK(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, kL0SmemBytes));
           XP_LAUNCH(k0, grid, 256, kL0SmemBytes, st, r);
+          if (n_long > 0) {
+            void (*k1)(const L0RowsArgs) = L.act == XPGNN_ACT_SIGMOID ? l0_rows_kernel<true, true> : l0_rows_kernel<false, true>;
+            XP_CHECK(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, kL0SmemBytes));
+            XP_LAUNCH(k1, n_long, 256, kL0SmemBytes, st, r);
+          }
         } else if (l == 0) {  // transform-first: gather the coalition-invariant Z
           s.n_chunks = L.h_out / cw;
           s.in = lay.zc; s.in_s_stride = 0; s.wgt = kind == XPGNN_CONV_GCN ? lay.wgt : nullptr;

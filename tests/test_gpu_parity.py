@@ -324,6 +324,36 @@ def test_compact_path_matches_oracle(kind, hidden, env, lib, monkeypatch):
 
 
 @pytest.mark.parametrize("kind", ["gcn", "sage"])
+def test_compact_path_hub_rows(kind, lib, monkeypatch):
+    """Destination rows above the long-row threshold (1024 in-edges) are processed by whole CTAs in the compact
+    path (hub rows of power-law graphs); same predictions as the oracle and as the tile path."""
+    from bikg_graph_explainability_public_b200.engine import GraphSpec, MaskedForward
+    from bikg_graph_explainability_public_b200.lowering import lower
+    from oracle.xpgnn_oracle import kernel_output
+
+    x, ei, arch, mask, q = _random_model_case(9, kind, n=4000, e=30000, f=32, hidden=(128, 128), s=40)
+    g = torch.Generator().manual_seed(5)
+    n = x.shape[0]
+    hubs = [q, 7, 1234]
+    extra = [torch.stack([torch.randint(0, n, (k,), generator=g), torch.full((k,), h)]) for h, k in zip(hubs, (2500, 3000, 1100))]
+    ei = torch.cat([ei] + extra, 1)
+    s = mask.shape[0]
+    mask[2, q] = True
+    mask[3, q] = False
+    _, y_ref = kernel_output(mask.numpy(), x, ei.numpy(), arch, q)
+    act = _pack(lib, mask)
+    gs = GraphSpec(x.cuda(), ei.cuda(), [0, n])
+    y = MaskedForward(gs, lower(arch), [q, 7])(act, s).cpu().numpy()
+    np.testing.assert_allclose(y[:, 0], y_ref.numpy().reshape(-1), rtol=Y_RTOL, atol=Y_ATOL)
+    _, y_ref7 = kernel_output(mask.numpy(), x, ei.numpy(), arch, 7)
+    np.testing.assert_allclose(y[:, 1], y_ref7.numpy().reshape(-1), rtol=Y_RTOL, atol=Y_ATOL)
+    monkeypatch.setenv("XPGNN_LONG", "0")   # hub rows through the row-per-warp kernels
+    np.testing.assert_allclose(MaskedForward(gs, lower(arch), [q, 7])(act, s).cpu().numpy(), y, rtol=2e-5, atol=1e-6)
+    monkeypatch.setenv("XPGNN_COMPACT", "0")
+    np.testing.assert_allclose(MaskedForward(gs, lower(arch), [q, 7])(act, s).cpu().numpy(), y, rtol=2e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("kind", ["gcn", "sage"])
 def test_bf16_transform_mode_within_tolerance(kind, lib):
     """precision="bf16": dense transforms on tcgen05 with bf16 operands (fp32 accumulate, fp32 storage).
     Bar from BASELINE.json north_star: predictions within 2e-2 relative."""
