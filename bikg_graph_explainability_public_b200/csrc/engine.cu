@@ -67,6 +67,8 @@ __global__ void __launch_bounds__(256) masked_scale_kernel(const int32_t* __rest
 // masked SpMM: one warp per destination row, lanes across the feature dimension, coalitions of
 // the tile looped inside so that the row's column indices / activity words are read once.
 // ------------------------------------------------------------------------------------------
+constexpr int kLongRowTile = 1024;  // in-edges above which the tile path hands a row to a whole CTA
+
 struct SpmmArgs {
   const int32_t* rowptr;
   const int32_t* col;
@@ -86,6 +88,7 @@ struct SpmmArgs {
   int64_t out_s_stride;
   int ld_out;
   int accumulate, act_fn, H;
+  int has_long_rows;         // the CSR has rows above kLongRowTile in-edges (host knows: max degree per unique CSR)
 };
 
 template <int VEC>
@@ -137,7 +140,10 @@ __device__ __forceinline__ void gather_edges(const SpmmArgs& a, uint32_t m, int 
   }
 }
 
-template <int VEC>
+// CTA_ROW: hub rows (more than long_threshold in-edges) -- a whole CTA takes the row and its warps split the coalition
+// slots, instead of one warp walking e.g. 82 K in-edges x 32 slots alone (the pruned last layer of a hub query is
+// exactly one such row).
+template <int VEC, bool CTA_ROW>
 __global__ void __launch_bounds__(256, 4) spmm_masked_kernel(const SpmmArgs a) {
   // Row-outer, coalition-inner: a row's column indices and edge-activity words are read once and stay
   // in registers for all coalitions of the tile (<= 64 in-edges; longer rows re-read them from L1).
@@ -145,10 +151,11 @@ __global__ void __launch_bounds__(256, 4) spmm_masked_kernel(const SpmmArgs a) {
   //  l1 23.7 -> 29.5 ms, l0 12.2 -> 29.9 ms -- see DESIGN.md.)
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const int chunks = (a.H + 32 * VEC - 1) / (32 * VEC);
-  for (int r = blockIdx.x * wpb + wib; r < a.n_rows; r += gridDim.x * wpb) {
+  for (int r = CTA_ROW ? blockIdx.x : blockIdx.x * wpb + wib; r < a.n_rows; r += CTA_ROW ? gridDim.x : gridDim.x * wpb) {
     const int v = a.rows ? a.rows[r] : a.row_lo + r;
     if (v < a.dst_lo || v >= a.dst_hi) continue;
     const int e0 = a.rowptr[v], e1 = a.rowptr[v + 1], deg = e1 - e0;
+    if (CTA_ROW ? deg <= kLongRowTile : deg > kLongRowTile) continue;  // hub rows belong to the CTA_ROW launch
     const float sc_lane = a.scale[(int64_t)v * 32 + lane];
     int u_reg[2] = {-1, -1};
     uint32_t bits_reg[2] = {0u, 0u};
@@ -165,7 +172,7 @@ __global__ void __launch_bounds__(256, 4) spmm_masked_kernel(const SpmmArgs a) {
     for (int cc = 0; cc < chunks; ++cc) {
       const int c0 = cc * 32 * VEC + lane * VEC;
       const bool colok = c0 < a.H;
-      for (int s = 0; s < a.n_bits; ++s) {
+      for (int s = CTA_ROW ? wib : 0; s < a.n_bits; s += CTA_ROW ? wpb : 1) {
         const int b = a.b0 + s;
         const float* in_s = a.in + (int64_t)s * a.in_s_stride;
         float acc[VEC];
@@ -334,6 +341,13 @@ __global__ void __launch_bounds__(128) head_kernel(const HeadArgs a, int max_dim
   }
 }
 
+__global__ void max_degree_kernel(const int32_t* __restrict__ rowptr, int lo, int hi, int32_t* __restrict__ out) {
+  const int v = lo + blockIdx.x * blockDim.x + threadIdx.x;
+  int d = v < hi ? rowptr[v + 1] - rowptr[v] : 0;
+  d = __reduce_max_sync(0xffffffffu, d);
+  if ((threadIdx.x & 31) == 0 && d > kLongRowTile) atomicMax(out, d);
+}
+
 __global__ void rows_by_hop_kernel(const int8_t* __restrict__ hop, int N, int max_hop, int32_t* __restrict__ rows, int32_t* __restrict__ count) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v < N && hop[v] >= 0 && hop[v] <= max_hop) rows[atomicAdd(count, 1)] = v;
@@ -369,8 +383,13 @@ static int launch_spmm(const SpmmArgs& s, cudaStream_t st) {
   const bool vec4 = (s.H % 4 == 0) && (s.ld_in % 4 == 0) && (s.ld_out % 4 == 0) && (s.in_s_stride % 4 == 0) &&
                     (s.out_s_stride % 4 == 0) && (((uintptr_t)s.in | (uintptr_t)s.out) % 16 == 0) &&
                     (!s.addend || (s.ld_add % 4 == 0 && (uintptr_t)s.addend % 16 == 0));
-  if (vec4) XP_LAUNCH(spmm_masked_kernel<4>, grid, 256, 0, st, s);
-  else XP_LAUNCH(spmm_masked_kernel<1>, grid, 256, 0, st, s);
+  void (*k)(const SpmmArgs) = vec4 ? spmm_masked_kernel<4, false> : spmm_masked_kernel<1, false>;
+  XP_LAUNCH(k, grid, 256, 0, st, s);
+  if (s.has_long_rows) {  // hub rows: one CTA per row, warps split the slots
+    const int grid_long = (int)std::min<int64_t>(s.n_rows, (int64_t)kNumSMs * 8);
+    void (*kl)(const SpmmArgs) = vec4 ? spmm_masked_kernel<4, true> : spmm_masked_kernel<1, true>;
+    XP_LAUNCH(kl, grid_long, 256, 0, st, s);
+  }
   return 0;
 }
 
@@ -531,6 +550,20 @@ int xpgnn_forward(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32_t
   for (int l = 0; l < NL; ++l) hmax = std::max(hmax, p->layers_host[l].h_out);
   const int64_t hstride = (int64_t)N * hmax;  // per-slot stride of the activation buffers
 
+  // ---- hub rows (a property of the graph): which CSRs have rows above kLongRowTile in-edges ----
+  std::vector<int32_t> max_deg(uniq.size(), 0);
+  {
+    Scratch sc(st);
+    XP_CHECK(sc.alloc(sizeof(int32_t) * uniq.size()));
+    XP_CHECK(cudaMemsetAsync(sc.p, 0, sizeof(int32_t) * uniq.size(), st));
+    for (size_t i = 0; i < uniq.size(); ++i) {
+      const int rows = uniq[i].hi - uniq[i].lo;
+      if (rows > 0) XP_LAUNCH(max_degree_kernel, (int)ceil_div(rows, 256), 256, 0, st, uniq[i].rowptr, uniq[i].lo, uniq[i].hi, sc.as<int32_t>() + i);
+    }
+    XP_CHECK(cudaMemcpyAsync(max_deg.data(), sc.p, sizeof(int32_t) * uniq.size(), cudaMemcpyDeviceToHost, st));
+    XP_CHECK(cudaStreamSynchronize(st));
+  }
+
   // ---- needed rows per layer (prune) ----
   std::vector<int> n_rows(NL, N);
   if (p->prune) {
@@ -622,7 +655,7 @@ int xpgnn_forward(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32_t
           const xpgnn_relation_t& R = L.rel_host[r];
           SpmmArgs s{};
           s.rowptr = R.rowptr; s.col = R.col; s.ebits = lay.ebits[umap[l][r]]; s.b0 = b0; s.n_bits = nb;
-          s.scale = lay.scale[umap[l][r]]; s.kind = R.conv_kind;
+          s.scale = lay.scale[umap[l][r]]; s.kind = R.conv_kind; s.has_long_rows = max_deg[umap[l][r]] > kLongRowTile;
           s.rows = p->prune ? lay.rows[l] : nullptr;
           s.n_rows = p->prune ? n_rows[l] : (R.dst_hi - R.dst_lo);
           s.row_lo = R.dst_lo; s.dst_lo = R.dst_lo; s.dst_hi = R.dst_hi;
