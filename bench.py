@@ -280,9 +280,11 @@ def config_dict(args, wl):
             "communities": wl.c, "coalitions_per_gpu_per_step": args.coalitions_per_gpu, "mode": "full (every conv layer "
             "over the whole-graph computational graph; per coalition only rows of active nodes are materialised, "
             "inactive rows are coalition invariant)", "l2": "inputs larger than L2 (activation tiles of "
-            "16 GiB vs 126 MB L2)", "precision": getattr(args, "precision", "fp32") + (
-                " (fp32 storage, dense transforms as 3xTF32 tcgen05 MMAs)" if getattr(args, "precision", "fp32") == "fp32"
-                else " transforms (fp32 storage, bf16 tcgen05 MMAs, fp32 accumulate)")}
+            "16 GiB vs 126 MB L2)", "precision": {
+                "fp32": "fp32 (fp32 storage, dense transforms as 3xTF32 tcgen05 MMAs)",
+                "bf16": "bf16 transforms (fp32 storage, bf16 tcgen05 MMAs, fp32 accumulate)",
+                "bf16_act": "bf16 transforms and bf16 activation storage (fp32 accumulate in the SpMM and the MMAs)",
+            }[getattr(args, "precision", "fp32")]}
 
 
 _REAL_STDOUT = None
@@ -314,8 +316,9 @@ def main():
     ap.add_argument("--cpu-coalitions", type=int, default=4, help="coalitions of the CPU baseline sample")
     ap.add_argument("--ref-coalitions", type=int, default=2, help="coalitions per step of --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"],
-                    help="fp32: TF32x3 tensor-core transforms (1e-4 parity bar); bf16: bf16 transforms (2e-2 bar)")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16", "bf16_act"],
+                    help="fp32: TF32x3 tensor-core transforms (1e-4 parity bar); bf16: bf16 transforms (2e-2 bar); "
+                         "bf16_act: bf16 transforms and bf16 activation storage (2e-2 bar)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -17,6 +17,7 @@
 //  4. GCN operands of layers >= 1 are stored pre-multiplied by deg^-1/2, so those gathers are
 //     unweighted sums; layer 0 gathers the coalition-invariant Z = X W^T with a per-source weight.
 #include <cub/device/device_scan.cuh>
+#include <cuda_bf16.h>
 
 #include <algorithm>
 #include <climits>
@@ -337,7 +338,8 @@ __device__ __forceinline__ void l0_fma(const float* __restrict__ w_rows, const f
 
 // LONG: one CTA per hub row -- the 8 warps take contiguous slices of the row's in-edges, the partial accumulators
 // are summed through shared memory in a fixed order (deterministic) and warp 0 runs the epilogue.
-template <bool SIGMOID, bool LONG>
+// OUT16: the activations of the tile are stored as bf16 in 64-element chunks (precision = bf16 activation storage).
+template <bool SIGMOID, bool LONG, bool OUT16>
 __global__ void __launch_bounds__(256, 2) l0_rows_kernel(const L0RowsArgs a) {
   extern __shared__ __align__(16) uint8_t l0_smem[];
   float(*s_w)[32][kL0WStride] = reinterpret_cast<float(*)[32][kL0WStride]>(l0_smem);
@@ -446,6 +448,9 @@ __global__ void __launch_bounds__(256, 2) l0_rows_kernel(const L0RowsArgs a) {
       // kept tiny (the kernel must stay inside the instruction cache): GCN and SAGE share one formula
       // (SAGE: self weight 0), ReLU / identity are a max with 0 / -inf
       float* outp = a.out + cm_off - (int64_t)a.b0 * a.out_s_stride;
+      // bf16 layout: one 64-column block is one chunk, a lane's 2 columns are one bf162
+      __nv_bfloat16* outp16 = reinterpret_cast<__nv_bfloat16*>(a.out) + (int64_t)cb * a.out_chunk_stride + (int64_t)v * 64 + lane * 2 -
+                              (int64_t)a.b0 * a.out_s_stride;
       uint32_t m = av;
 #pragma unroll
       for (int k = 0; k < 32; ++k) {
@@ -463,7 +468,8 @@ __global__ void __launch_bounds__(256, 2) l0_rows_kernel(const L0RowsArgs a) {
             o.x = fmaxf(o.x, lower); o.y = fmaxf(o.y, lower);
           }
           o.x *= pv; o.y *= pv;
-          __stcs(reinterpret_cast<float2*>(outp + (int64_t)b * a.out_s_stride), o);
+          if (OUT16) *reinterpret_cast<__nv_bfloat162*>(outp16 + (int64_t)b * a.out_s_stride) = __floats2bfloat162_rn(o.x, o.y);
+          else __stcs(reinterpret_cast<float2*>(outp + (int64_t)b * a.out_s_stride), o);
         }
       }
     }
@@ -689,6 +695,85 @@ __global__ void __launch_bounds__(256) cspmm_long_kernel(const CspmmArgs a) {
   }
 }
 
+// bf16 activation storage: the same list-driven pass over 64-element (128-byte) chunks of bf16 rows; 8 lanes x 8
+// elements per row, fp32 accumulation, aggregate written back as bf16 (layers >= 1 only: no weights, addend or activation).
+__device__ __forceinline__ void add_bf16x8(const uint4& q, float (&acc)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    acc[2 * i] += f.x;
+    acc[2 * i + 1] += f.y;
+  }
+}
+
+__global__ void __launch_bounds__(256, 6) cspmm16_kernel(const CspmmArgs a) {
+  __shared__ int s_start[33];
+  __shared__ int s_item;
+  if (threadIdx.x <= a.nb) s_start[threadIdx.x] = a.slot_tile_start[threadIdx.x];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane & 7, grp = lane >> 3;
+  const int total = s_start[a.nb] * a.n_chunks;
+  const __nv_bfloat16* in16 = reinterpret_cast<const __nv_bfloat16*>(a.in);
+  __nv_bfloat16* out16 = reinterpret_cast<__nv_bfloat16*>(a.out);
+  int t = 0;
+  while (true) {
+    if (threadIdx.x == 0) s_item = atomicAdd(a.counter, 1);
+    __syncthreads();
+    const int idx = s_item;
+    __syncthreads();
+    if (idx >= total) break;
+    while (idx >= s_start[t + 1] * a.n_chunks) ++t;
+    const int ntb = s_start[t + 1] - s_start[t];
+    const int rem = idx - s_start[t] * a.n_chunks;
+    const int c = rem / ntb, tb = rem - c * ntb;
+    const int n_act = a.slot_info[t].x;
+    const int32_t* al = a.act_list + (int64_t)t * a.N;
+    const uint32_t* rp = a.rowptr_c + (int64_t)t * (a.N + 1);
+    const int32_t* cc = a.ccol + a.slot_base[t];
+    const __nv_bfloat16* in_c = in16 + (int64_t)t * a.in_s_stride + (int64_t)c * a.in_chunk_stride + sub * 8;
+    __nv_bfloat16* out_c = out16 + (int64_t)t * a.out_s_stride + (int64_t)c * a.out_chunk_stride + sub * 8;
+#pragma unroll 1
+    for (int it = 0; it < 4; ++it) {
+      const int i = tb * 128 + it * 32 + warp * 4 + grp;
+      const bool valid = i < n_act;
+      int v = 0;
+      uint32_t e0 = 0, cnt = 0;
+      if (valid) {
+        v = __ldcs(al + i);
+        e0 = __ldcs(rp + i);
+        cnt = __ldcs(rp + i + 1) - e0;
+      }
+      const uint32_t maxcnt = __reduce_max_sync(0xffffffffu, cnt);
+      float acc[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = 0.0f;
+      for (uint32_t base = 0; base < maxcnt; base += 8) {
+        const int my = base + sub < cnt ? __ldcs(cc + e0 + base + sub) : -1;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int u = __shfl_sync(0xffffffffu, my, grp * 8 + j);
+          if (u >= 0) add_bf16x8(__ldg(reinterpret_cast<const uint4*>(in_c + (int64_t)u * 64)), acc);
+        }
+      }
+      if (valid) {
+        float scale;
+        if (a.kind == XPGNN_CONV_GCN) {  // operands are already scaled by deg^-1/2: agg = dinv (sum + self)
+          scale = gcn_dinv(cnt);
+          add_bf16x8(__ldg(reinterpret_cast<const uint4*>(in_c + (int64_t)v * 64)), acc);
+        } else {
+          scale = 1.0f / (float)max(cnt, 1u);
+        }
+        uint4 o;
+        __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) oh[k] = __floats2bfloat162_rn(acc[2 * k] * scale, acc[2 * k + 1] * scale);
+        __stcs(reinterpret_cast<uint4*>(out_c + (int64_t)v * 64), o);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // head on the query rows; an inactive query takes the isolated-node chain (coalition invariant)
 // ------------------------------------------------------------------------------------------
@@ -705,7 +790,7 @@ struct CHeadArgs {
   xpgnn_dense_t head[kMaxHeadC];
   const float* in;                  // last conv output, chunk-major
   int64_t in_s_stride, in_chunk_stride;
-  int dim0, cw, cw_lg;
+  int dim0, cw, cw_lg, in16;        // in16: bf16 activations in 64-element chunks
   const int32_t* query;
   int n_query, out_col;
   float* y;                         // y[slot * n_query + q]
@@ -732,8 +817,13 @@ __global__ void __launch_bounds__(128) compact_head_kernel(const CHeadArgs a, in
   const int qv = a.query[q];
   const bool active = (a.act[(int64_t)qv * a.W + a.w] >> (a.b0 + slot)) & 1u;
   if (active) {
-    const float* src = a.in + (int64_t)slot * a.in_s_stride + (int64_t)qv * a.cw;
-    for (int i = threadIdx.x; i < a.dim0; i += blockDim.x) x0[i] = src[(int64_t)(i >> a.cw_lg) * a.in_chunk_stride + (i & (a.cw - 1))];
+    if (a.in16) {
+      const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(a.in) + (int64_t)slot * a.in_s_stride + (int64_t)qv * 64;
+      for (int i = threadIdx.x; i < a.dim0; i += blockDim.x) x0[i] = __bfloat162float(src[(int64_t)(i >> 6) * a.in_chunk_stride + (i & 63)]);
+    } else {
+      const float* src = a.in + (int64_t)slot * a.in_s_stride + (int64_t)qv * a.cw;
+      for (int i = threadIdx.x; i < a.dim0; i += blockDim.x) x0[i] = src[(int64_t)(i >> a.cw_lg) * a.in_chunk_stride + (i & (a.cw - 1))];
+    }
     __syncthreads();
   } else {
     for (int i = threadIdx.x; i < a.h0; i += blockDim.x) {
@@ -785,6 +875,15 @@ bool compact_eligible(const xpgnn_plan_t* p) {
     if (l > 0 && L.h_in != p->layers_host[l - 1].h_out) return false;
   }
   return true;
+}
+
+// bf16 activation storage (plan precision 2): GCN stacks whose widths are multiples of 64 (one bf16 chunk = 64 elements);
+// anything else keeps fp32 storage with bf16 tensor-core transforms (precision 1 semantics)
+static bool compact_act16(const xpgnn_plan_t* p) {
+  if (p->precision != 2 || p->layers_host[0].rel_host[0].conv_kind != XPGNN_CONV_GCN) return false;
+  for (int l = 0; l < p->n_layers; ++l)
+    if (p->layers_host[l].h_out % 64 || p->layers_host[l].h_out > 256) return false;
+  return !(getenv("XPGNN_L0") && std::string(getenv("XPGNN_L0")) == "lists");
 }
 
 struct CLayout {
@@ -841,10 +940,11 @@ static CLayout compact_carve(const xpgnn_plan_t* p, void* ws, int64_t cap, int t
   c.rows_packed = b.take<int32_t>((int64_t)tile * ceil_div(N, 128) * 128);
   c.rs_packed = b.take<float>((int64_t)tile * ceil_div(N, 128) * 128);
   c.ccol = b.take<int32_t>((int64_t)tile * E);
-  c.hbuf[0] = b.take<float>((int64_t)tile * N * hmax);
+  const int64_t act_floats = compact_act16(p) ? ((int64_t)tile * N * hmax + 1) / 2 : (int64_t)tile * N * hmax;  // bf16: half
+  c.hbuf[0] = b.take<float>(act_floats);
   if (NL > 1) {
-    c.hbuf[1] = b.take<float>((int64_t)tile * N * hmax);
-    c.agg = b.take<float>((int64_t)tile * N * hmax);
+    c.hbuf[1] = b.take<float>(act_floats);
+    c.agg = b.take<float>(act_floats);
   }
   c.bytes = (b.off + 255) & ~255ll;
   return c;
@@ -896,6 +996,8 @@ int forward_compact(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32
   // row-outer layer 0 (Z row-major) when a warp can own 128 columns; else the list-driven kernel (Z chunk-major)
   const bool l0_lists = getenv("XPGNN_L0") && std::string(getenv("XPGNN_L0")) == "lists";
   const bool l0_rows = !l0_lists && cw == 32 && L0.h_out % 64 == 0;
+  const bool act16 = compact_act16(p) && l0_rows;   // bf16 activation storage
+  const int64_t cstride16 = (int64_t)N * 64;        // chunk stride of the bf16 layout (elements)
   {
     DenseArgs z{};
     z.in = p->x; z.ld_in = p->f_in; z.k = p->f_in; z.w = R0.w_nbr; z.n_out = L0.h_out; z.out = lay.zc;
@@ -981,11 +1083,15 @@ int forward_compact(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32
           ProfScope ps(PROF_SPMM_INVARIANT, st);
           const int grid = (int)std::min<int64_t>(ceil_div(N, 8 * kRowGrab), (int64_t)kNumSMs * 2);
           r.long_rows = lay.long_rows; r.long_threshold = n_long > 0 ? kLongRow : 0; r.counter = lay.counters + 13;
-          void (*k0)(const L0RowsArgs) = L.act == XPGNN_ACT_SIGMOID ? l0_rows_kernel<true, false> : l0_rows_kernel<false, false>;
+          const bool sg = L.act == XPGNN_ACT_SIGMOID;
+          if (act16) r.out_chunk_stride = cstride16;
+          void (*k0)(const L0RowsArgs) = act16 ? (sg ? l0_rows_kernel<true, false, true> : l0_rows_kernel<false, false, true>)
+                                               : (sg ? l0_rows_kernel<true, false, false> : l0_rows_kernel<false, false, false>);
           XP_CHECK(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, kL0SmemBytes));
           XP_LAUNCH(k0, grid, 256, kL0SmemBytes, st, r);
           if (n_long > 0) {
-            void (*k1)(const L0RowsArgs) = L.act == XPGNN_ACT_SIGMOID ? l0_rows_kernel<true, true> : l0_rows_kernel<false, true>;
+            void (*k1)(const L0RowsArgs) = act16 ? (sg ? l0_rows_kernel<true, true, true> : l0_rows_kernel<false, true, true>)
+                                                 : (sg ? l0_rows_kernel<true, true, false> : l0_rows_kernel<false, true, false>);
             XP_CHECK(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, kL0SmemBytes));
             XP_LAUNCH(k1, n_long, 256, kL0SmemBytes, st, r);
           }
@@ -996,6 +1102,26 @@ int forward_compact(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32
           else s.bias = R.b_nbr;
           s.out = cur; s.act_fn = L.act; s.prescale = next_gcn;
           if (launch_cspmm(s, cw, st)) return 1;
+        } else if (act16) {  // bf16 storage: aggregate (bf16 in, fp32 accumulate, bf16 out), then the bf16 tensor-core transform
+          s.n_chunks = L.h_in / 64;
+          s.in = cur; s.in_s_stride = hstride; s.in_chunk_stride = cstride16;
+          s.out = lay.agg; s.out_chunk_stride = cstride16;
+          {
+            ProfScope ps(PROF_SPMM_TILE, st);
+            int per_sm = 0;
+            XP_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cspmm16_kernel, 256, 0));
+            XP_LAUNCH(cspmm16_kernel, kNumSMs * std::max(per_sm, 1), 256, 0, st, s);
+          }
+          DenseArgs d{};
+          d.in = lay.agg; d.in_s_stride = hstride; d.ld_in = 64; d.k = L.h_in; d.cw_in = 64; d.cw_in_lg = 6; d.in_chunk_stride = cstride16;
+          d.w = R.w_nbr; d.b = R.b_nbr; d.n_out = L.h_out;
+          d.out = nxt; d.out_s_stride = hstride; d.ld_out = 64; d.cw_out = 64; d.cw_out_lg = 6; d.out_chunk_stride = cstride16;
+          d.rows_packed = lay.rows_packed; d.n_tiles_dev = lay.n_tiles;
+          d.rows_per_s = N; d.M = (int64_t)nb * ceil_div(N, 128) * 128; d.dst_lo = 0; d.dst_hi = N;
+          d.act_fn = L.act; d.rs_packed = next_gcn ? lay.rs_packed : nullptr;
+          d.in16 = 1; d.out16 = 1;
+          if (launch_dense(d, st, DENSE_TC_BF16)) return 1;
+          std::swap(cur, nxt);
         } else {       // aggregate-first, then the dense transform of the active rows
           s.n_chunks = L.h_in / cw;
           s.in = cur; s.in_s_stride = hstride; s.wgt = nullptr; s.addend = nullptr;
@@ -1037,7 +1163,7 @@ int forward_compact(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32
         h.head[i] = p->head_host[i];
         max_dim = std::max(max_dim, std::max(p->head_host[i].in, p->head_host[i].out));
       }
-      h.in = cur; h.in_s_stride = hstride; h.in_chunk_stride = cstride; h.dim0 = p->layers_host[NL - 1].h_out; h.cw = cw; h.cw_lg = cw_lg;
+      h.in = cur; h.in_s_stride = hstride; h.in_chunk_stride = cstride; h.dim0 = p->layers_host[NL - 1].h_out; h.cw = cw; h.cw_lg = cw_lg; h.in16 = act16; if (act16) h.in_chunk_stride = cstride16;
       h.query = p->query; h.n_query = p->n_query; h.out_col = p->out_col;
       h.y = y + ((int64_t)(w * 32 + b0) - s0) * p->n_query;
       h.act = act; h.W = W; h.w = w; h.b0 = b0;

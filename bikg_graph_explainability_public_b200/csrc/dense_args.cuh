@@ -36,6 +36,8 @@ struct DenseArgs {
   const int32_t* rows_packed;
   const int32_t* n_tiles_dev;
   const float* rs_packed;      // optional row scale per entry: (1 + masked in-degree)^-1/2 (GCN operand of the next layer)
+  // ---- bf16 activation storage (tensor-core bf16 mode only): `in` / `out` point at __nv_bfloat16, all strides in elements ----
+  int in16, out16;
 };
 constexpr int kPackShift = 26;  // node ids < 2^26 in the packed tile table
 

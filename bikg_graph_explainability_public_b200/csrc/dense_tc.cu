@@ -305,7 +305,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const DenseArgs
         cur_ti = ti;
       }
       float4 buf[8];
-      {
+      if (MODE == 1 && a.in16) {
+        // bf16 operand: one 16-byte column (8 elements) per row and thread, no conversion; ld_row holds element offsets
+        const int64_t o16 = dense_in_off(a, kc * KC + lj * 8);
+        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+          buf[p] = ld_row[p] ? __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const __nv_bfloat16*>(a.in) + (ld_row[p] - a.in) + o16)) : zero;
+      } else {
         const int64_t o0 = dense_in_off(a, kc * KC + j0 * 4), o1 = dense_in_off(a, kc * KC + j1 * 4);
         const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -336,6 +343,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const DenseArgs
           split_tf32(buf[2 * p + 1], hi, lo);
           *reinterpret_cast<float4*>(stage + core_off(r, lj + 4, Cfg::K16)) = hi;
           *reinterpret_cast<float4*>(stage + Cfg::PART_BYTES + core_off(r, lj + 4, Cfg::K16)) = lo;
+        } else if (a.in16) {
+          *reinterpret_cast<float4*>(stage + core_off(r, lj, Cfg::K16)) = buf[p];
         } else {
           const uint2 p0 = pack_bf16(buf[2 * p]), p1 = pack_bf16(buf[2 * p + 1]);
           *reinterpret_cast<uint4*>(stage + core_off(r, lj, Cfg::K16)) = make_uint4(p0.x, p0.y, p1.x, p1.y);
@@ -465,7 +474,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const DenseArgs
             float4 v[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const float4*>(s_t + (i * 8 + (lane >> 2)) * TR_STRIDE + cq);
-            if (a.accumulate) {
+            if (a.accumulate && !a.out16) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 if (oo_r[i] < 0) continue;
@@ -483,9 +492,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const DenseArgs
               }
               v[i].x *= rs_r[i]; v[i].y *= rs_r[i]; v[i].z *= rs_r[i]; v[i].w *= rs_r[i];
             }
+            if (a.out16) {
+              __nv_bfloat16* out16 = reinterpret_cast<__nv_bfloat16*>(a.out);
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              if (oo_r[i] >= 0) *reinterpret_cast<float4*>(a.out + oo_r[i] + ooff) = v[i];
+              for (int i = 0; i < 4; ++i)
+                if (oo_r[i] >= 0) *reinterpret_cast<uint2*>(out16 + oo_r[i] + ooff) = pack_bf16(v[i]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (oo_r[i] >= 0) *reinterpret_cast<float4*>(a.out + oo_r[i] + ooff) = v[i];
+            }
           }
         } else if (ok) {
           scalar_epilogue(s_t + lane * TR_STRIDE, c0, a.n_out, s_bias, a.out + oo, a.cw_out, a.cw_out_lg, a.out_chunk_stride, a.accumulate,
@@ -521,6 +537,8 @@ static int tc_stages(const DenseArgs& d, int mode) {
 
 static bool tc_eligible(const DenseArgs& d, int mode) {
   if (d.k <= 0 || d.k % KC != 0 || d.n_out < 8 || d.n_out > 256) return false;
+  // bf16 storage: bf16 MMA mode, tile table rows, float4-able output, no accumulate into a bf16 destination
+  if ((d.in16 || d.out16) && (mode != 1 || d.accumulate || (d.n_out & 3) || (d.ld_in & 7) || (d.in_chunk_stride & 7))) return false;
   if (d.M >= (1ll << 31) - 256 || d.rows_per_s <= 0) return false;
   if (d.ld_in % 4 != 0 || d.in_s_stride % 4 != 0 || d.in_chunk_stride % 4 != 0 || ((uintptr_t)d.in & 15) != 0 || ((uintptr_t)d.w & 15) != 0)
     return false;

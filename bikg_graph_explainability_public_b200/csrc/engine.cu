@@ -367,10 +367,11 @@ Profile g_prof;
 int launch_dense(const DenseArgs& d, cudaStream_t st, int precision) {
   if (d.M <= 0 || d.n_out <= 0) return 0;
   ProfScope ps(PROF_DENSE, st);
-  if (precision != DENSE_SIMT && d.M >= 1024) {
+  if (precision != DENSE_SIMT && (d.M >= 1024 || d.in16 || d.out16)) {
     const int mode = precision == DENSE_TC_BF16 ? 1 : 0;
     if (dense_tc_eligible(d, mode)) return launch_dense_tc(d, mode, st);
   }
+  XP_REQUIRE(!d.in16 && !d.out16, "bf16 activation storage needs the tensor-core transform (shape not eligible)");
   dim3 grid((unsigned)(2 * ceil_div(d.M, 2 * DBM)), (unsigned)ceil_div(d.n_out, DBN));
   XP_LAUNCH(dense_rows_kernel, grid, 256, 0, st, d);
   return 0;
@@ -528,10 +529,10 @@ int xpgnn_forward(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32_t
   XP_REQUIRE(p->n_layers >= 1 && p->n_nodes > 0 && p->n_query > 0 && p->query, "empty plan");
   XP_REQUIRE(s0 % 32 == 0 && n_s >= 0 && (int64_t)W * 32 >= (int64_t)s0 + n_s, "coalition range outside the bit matrix");
   XP_REQUIRE(p->n_head <= kMaxHead, "head deeper than 8 layers");
-  XP_REQUIRE(p->precision == 0 || p->precision == 1, "plan precision must be 0 (fp32) or 1 (bf16 transforms)");
+  XP_REQUIRE(p->precision >= 0 && p->precision <= 2, "plan precision must be 0 (fp32), 1 (bf16 transforms) or 2 (bf16 transforms + bf16 activation storage)");
   // fp32 plans use the 3xTF32 tensor-core transform (error ~2^-20) unless XPGNN_DENSE=simt forces exact FMA
   const char* dense_env = getenv("XPGNN_DENSE");
-  const int dense_prec = p->precision == 1 ? DENSE_TC_BF16
+  const int dense_prec = p->precision >= 1 ? DENSE_TC_BF16
                                            : ((dense_env && std::string(dense_env) == "simt") ? DENSE_SIMT : DENSE_TC_TF32X3);
   XP_REQUIRE(!p->prune || p->hop, "prune = 1 needs the hop levels");
   if (n_s == 0) return 0;

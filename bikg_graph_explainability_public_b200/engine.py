@@ -143,7 +143,7 @@ class MaskedForward:
         p.n_query, p.query, p.out_col = int(q.numel()), q.data_ptr(), int(out_col)
         p.prune, p.hop = int(bool(prune)), _lib.dptr(hop_t)
         p.zero_edge_rule = int(bool(zero_edge_rule))
-        p.precision = {"fp32": 0, "bf16": 1}[precision]
+        p.precision = {"fp32": 0, "bf16": 1, "bf16_act": 2}[precision]
         self.plan, self.n_query, self.device = p, int(q.numel()), dev
         self.stats = torch.zeros(4, dtype=torch.int64, device=dev)
         # workspace: the largest coalition tile that fits

@@ -374,6 +374,27 @@ def test_bf16_transform_mode_within_tolerance(kind, lib):
     np.testing.assert_allclose(y, y_ref.numpy().reshape(-1), rtol=2e-2, atol=2e-3)
 
 
+def test_bf16_activation_storage_within_tolerance(lib):
+    """precision="bf16_act": bf16 tensor-core transforms and bf16 storage of the per-coalition activations in the
+    compact path (fp32 accumulation everywhere).  Bar from BASELINE.json north_star: predictions within 2e-2 relative."""
+    from bikg_graph_explainability_public_b200.engine import GraphSpec, MaskedForward
+    from bikg_graph_explainability_public_b200.lowering import lower
+    from oracle.xpgnn_oracle import kernel_output
+
+    x, ei, arch, mask, q = _random_model_case(6, "gcn", n=3000, e=30000, f=64, hidden=(128, 128), s=70)
+    s, n = mask.shape
+    _, y_ref = kernel_output(mask.numpy(), x, ei.numpy(), arch, q)
+    act = _pack(lib, mask)
+    g = GraphSpec(x.cuda(), ei.cuda(), [0, n])
+    y = MaskedForward(g, lower(arch), [q], precision="bf16_act")(act, s)[:, 0].cpu().numpy()
+    np.testing.assert_allclose(y, y_ref.numpy().reshape(-1), rtol=2e-2, atol=2e-3)
+    y32 = MaskedForward(g, lower(arch), [q], precision="fp32")(act, s)[:, 0].cpu().numpy()
+    assert np.max(np.abs(y - y32)) > 0, "the bf16 storage path was not taken"
+    # memory-limited tiles and sub-ranges give the same numbers
+    y8 = MaskedForward(g, lower(arch), [q], precision="bf16_act", tile_coalitions=8)(act, s)[:, 0].cpu().numpy()
+    np.testing.assert_allclose(y8, y, rtol=1e-6, atol=1e-7)
+
+
 def test_wlm_fit_matches_closed_form(lib):
     """Fit kernels vs the oracle's torch-autograd port on random data, both target layouts."""
     from bikg_graph_explainability_public_b200 import _lib
