@@ -414,7 +414,8 @@ def main():
         visits = eng.edge_visits_per_coalition  # kept edges x conv layers
         # algorithmic bytes of one coalition-layer: col idx + rowptr + bits + read Z once + write
         e_kept = eng.edges_per_layer[0]
-        b_alg = 4 * e_kept + 4 * (n + 1) + n / 8 + 2 * n * h * 4
+        elt = 2 if args.precision == "bf16_act" else 4  # bytes per stored activation element
+        b_alg = 4 * e_kept + 4 * (n + 1) + n / 8 + 2 * n * h * elt
         cats = ["masked_degree", "spmm_invariant_l0", "spmm_tile_l1", "dense", "head", "compaction"]
         kern = {k: {"ms": float(prof_ms[0][i]), "launches": int(prof_ms[1][i])} for i, k in enumerate(cats)}
         peaks = {}
@@ -436,7 +437,7 @@ def main():
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-                traffic = json.load(fh).get(dom)
+                traffic = json.load(fh).get(dom) if args.precision != "bf16_act" else None
         except OSError:
             pass
         line = {
@@ -452,7 +453,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
             "roofline": {"bound": "hbm", "kernel": "%s (%s)" % (
-                ("cspmm_kernel" if dom == "spmm_tile_l1" else "l0_rows_kernel") if kern["compaction"]["launches"]
+                (("cspmm16_kernel" if args.precision == "bf16_act" else "cspmm_kernel") if dom == "spmm_tile_l1" else "l0_rows_kernel")
+                if kern["compaction"]["launches"]
                 else "spmm_masked_kernel", dom),
                          "achieved": roof.get(dom, {}).get("achieved_gbs"), "peak": peak, "unit": "GB/s",
                          "frac": roof.get(dom, {}).get("frac"), "traffic": traffic,

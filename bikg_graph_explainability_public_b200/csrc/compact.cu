@@ -707,7 +707,8 @@ __device__ __forceinline__ void add_bf16x8(const uint4& q, float (&acc)[8]) {
   }
 }
 
-__global__ void __launch_bounds__(256, 6) cspmm16_kernel(const CspmmArgs a) {
+template <int OCC>
+__global__ void __launch_bounds__(256, OCC) cspmm16_kernel(const CspmmArgs a) {
   __shared__ int s_start[33];
   __shared__ int s_item;
   if (threadIdx.x <= a.nb) s_start[threadIdx.x] = a.slot_tile_start[threadIdx.x];
@@ -1108,9 +1109,11 @@ int forward_compact(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32
           s.out = lay.agg; s.out_chunk_stride = cstride16;
           {
             ProfScope ps(PROF_SPMM_TILE, st);
+            const int occ16 = getenv("XPGNN_OCC16") ? atoi(getenv("XPGNN_OCC16")) : 8;
+            void (*k16)(const CspmmArgs) = occ16 >= 8 ? cspmm16_kernel<8> : (occ16 <= 4 ? cspmm16_kernel<4> : cspmm16_kernel<6>);
             int per_sm = 0;
-            XP_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cspmm16_kernel, 256, 0));
-            XP_LAUNCH(cspmm16_kernel, kNumSMs * std::max(per_sm, 1), 256, 0, st, s);
+            XP_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k16, 256, 0));
+            XP_LAUNCH(k16, kNumSMs * std::max(per_sm, 1), 256, 0, st, s);
           }
           DenseArgs d{};
           d.in = lay.agg; d.in_s_stride = hstride; d.ld_in = 64; d.k = L.h_in; d.cw_in = 64; d.cw_in_lg = 6; d.in_chunk_stride = cstride16;
