@@ -341,6 +341,11 @@ __global__ void __launch_bounds__(128) head_kernel(const HeadArgs a, int max_dim
   }
 }
 
+__global__ void add_into_kernel(float* __restrict__ acc, const float* __restrict__ x, int n, int first) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) acc[i] = first ? x[i] : acc[i] + x[i];
+}
+
 __global__ void max_degree_kernel(const int32_t* __restrict__ rowptr, int lo, int hi, int32_t* __restrict__ out) {
   const int v = lo + blockIdx.x * blockDim.x + threadIdx.x;
   int d = v < hi ? rowptr[v + 1] - rowptr[v] : 0;
@@ -403,6 +408,7 @@ struct Layout {
   float* hbuf[2] = {nullptr, nullptr};
   float* agg = nullptr;
   std::vector<std::vector<float*>> wimg;  // per layer >= 1, per relation: TF32 hi/lo image of W for the fused kernel
+  std::vector<std::vector<float*>> wroot; // per layer >= 1, per relation: sum of the SAGE root weights of its destination group
   std::vector<int32_t*> rows;  // per layer (prune)
   int32_t* row_counts = nullptr;
   int64_t bytes = 0;
@@ -459,6 +465,10 @@ static Layout carve(const xpgnn_plan_t* p, void* ws, int64_t cap, int tile, cons
     lay.hbuf[1] = b.take<float>((int64_t)tile * N * hmax);
     lay.agg = b.take<float>((int64_t)tile * N * kmax);
   }
+  lay.wroot.resize(p->n_layers);
+  for (int l = 1; l < p->n_layers; ++l)
+    for (int r = 0; r < p->layers_host[l].n_rel; ++r)
+      lay.wroot[l].push_back(b.take<float>((int64_t)p->layers_host[l].h_out * p->layers_host[l].h_in));
   lay.wimg.resize(p->n_layers);
   for (int l = 1; l < p->n_layers; ++l)
     for (int r = 0; r < p->layers_host[l].n_rel; ++r)
@@ -633,6 +643,29 @@ int xpgnn_forward(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32_t
     }
   }
 
+  // HeteroConv(sum) adds W_root,r x[v] once per relation into the same destination type: one transform with the summed
+  // root weights per destination group instead (at C4: 15 of the 40 dense launches of a layer)
+  std::vector<std::vector<char>> group_root(NL);
+  for (int l = 1; l < NL; ++l) {
+    const xpgnn_layer_t& L = p->layers_host[l];
+    std::vector<char> first, last;
+    first_last(L, first, last);
+    group_root[l].assign(L.n_rel, 0);
+    for (int r = 0; r < L.n_rel; ++r) {
+      if (!last[r]) continue;
+      int n_root = 0;
+      const int nw = L.h_out * L.h_in;
+      for (int q = 0; q <= r; ++q) {
+        const xpgnn_relation_t& Q = L.rel_host[q];
+        if (Q.dst_lo != L.rel_host[r].dst_lo || Q.dst_hi != L.rel_host[r].dst_hi) continue;
+        if (Q.conv_kind != XPGNN_CONV_SAGE_MEAN || !Q.w_root) continue;
+        XP_LAUNCH(add_into_kernel, (int)ceil_div(nw, 256), 256, 0, st, lay.wroot[l][r], Q.w_root, nw, n_root == 0);
+        ++n_root;
+      }
+      group_root[l][r] = n_root > 0;
+    }
+  }
+
   const int w_first = s0 / 32, w_last = (s0 + n_s - 1) / 32;
   for (int w = w_first; w <= w_last; ++w) {
     const int bits_in_word = std::min(32, s0 + n_s - w * 32);
@@ -681,7 +714,7 @@ int xpgnn_forward(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32_t
             s.out = lay.agg; s.out_s_stride = (int64_t)N * L.h_in; s.ld_out = L.h_in;
             s.accumulate = 0; s.act_fn = XPGNN_ACT_NONE;
             if (launch_spmm(s, st)) return 1;
-            const bool sage_root = R.conv_kind == XPGNN_CONV_SAGE_MEAN && R.w_root;
+            const bool sage_root = last[r] && group_root[l][r];  // merged root transform of the destination group
             DenseArgs d{};
             d.in = lay.agg; d.in_s_stride = (int64_t)N * L.h_in; d.ld_in = L.h_in; d.k = L.h_in; d.w = R.w_nbr; d.b = R.b_nbr;
             d.n_out = L.h_out; d.out = nxt; d.out_s_stride = hstride; d.ld_out = hmax;
@@ -693,8 +726,8 @@ int xpgnn_forward(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32_t
             if (launch_dense(d, st, dense_prec)) return 1;
             if (sage_root) {
               DenseArgs rt = d;
-              rt.in = cur; rt.in_s_stride = hstride; rt.ld_in = hmax; rt.w = R.w_root; rt.b = nullptr;
-              rt.accumulate = 1; rt.act_fn = last[r] ? L.act : XPGNN_ACT_NONE;
+              rt.in = cur; rt.in_s_stride = hstride; rt.ld_in = hmax; rt.w = lay.wroot[l][r]; rt.b = nullptr;
+              rt.accumulate = 1; rt.act_fn = L.act;
               if (launch_dense(rt, st, dense_prec)) return 1;
             }
           }
