@@ -434,10 +434,19 @@ def main():
                 avg_ms = kern[k]["ms"] / kern[k]["launches"]
                 ach = tile * b_alg / (avg_ms / 1e3) / 1e9
                 roof[k] = {"avg_launch_ms": avg_ms, "achieved_gbs": ach, "frac": ach / peak}
-        traffic = None
+        traffic, fabric = None, None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-                traffic = json.load(fh).get(dom) if args.precision != "bf16_act" else None
+                tj = json.load(fh)
+            if args.precision == "fp32" and args.workload == "c3":
+                traffic = tj.get(dom)
+                # the binding resource of the layer >= 1 SpMM is the L2 -> SM fabric, not HBM: report it next to the roofline
+                if dom == "spmm_tile_l1" and "spmm_tile_l1_xbar_bytes" in tj and roof.get(dom):
+                    ach = tj["spmm_tile_l1_xbar_bytes"] * (tile / 32.0) / (roof[dom]["avg_launch_ms"] / 1e3) / 1e9
+                    fabric = {"bytes_per_launch": tj["spmm_tile_l1_xbar_bytes"] * (tile / 32.0), "achieved_gbs": ach,
+                              "peak_gbs": tj["l2_fabric_peak_gbs"], "frac": ach / tj["l2_fabric_peak_gbs"],
+                              "source": "l1tex__m_xbar2l1tex_read_bytes.sum of one launch (ncu, profiles/r01_summary.md) / "
+                                        "live launch time; peak = tools/gather_probe.cu"}
         except OSError:
             pass
         line = {
@@ -460,7 +469,7 @@ def main():
                          "frac": roof.get(dom, {}).get("frac"), "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                          "algorithmic_bytes_per_launch": tile * b_alg, "coalitions_per_launch": tile,
-                         "per_kernel": roof},
+                         "per_kernel": roof, "l2_fabric": fabric},
             "kernels": kern,
             "kernel_share_of_step": share,
         }

@@ -170,7 +170,10 @@ typedef struct {
                                  1: only rows whose value can reach a query                  */
   const int8_t* hop;          /* [N] BFS level from the queries (needed when prune = 1)        */
   int32_t zero_edge_rule;     /* 1: a coalition with no active edge yields 0 (model.py:213-215) */
-  int32_t precision;          /* 0: fp32 everywhere; 1: bf16 tcgen05 for the dense transforms   */
+  int32_t precision;          /* 0: fp32 storage, transforms as 3xTF32 tcgen05 MMAs (1e-4 bar);
+                                 1: fp32 storage, bf16 tcgen05 transforms (2e-2 bar);
+                                 2: bf16 transforms + bf16 storage of the per-coalition activations where the
+                                    compact path supports it (GCN stacks, widths % 64 == 0), else as 1 */
 } xpgnn_plan_t;
 
 /* Bytes of scratch xpgnn_forward needs to process `tile_coalitions` (1..32, power of two)
