@@ -43,6 +43,10 @@ WORKLOADS = {
                type_frac=(0.4, 0.25, 0.15, 0.1, 0.1), relations=20),
     # configs[4]: scale sweep graph, 64 batched query nodes
     "c5": dict(kind="homo_gcn", nodes=5_000_000, edges=100_000_000, features=128, hidden=128, communities=500, queries=64),
+    # configs[1] at scale: ONE node type, 3 relations (edges round-robin), HeteroConv(GCNConv) + MLP head
+    "c2_100k": dict(kind="hetero_gcn1", nodes=100_000, edges=2_000_000, features=84, hidden=16, communities=50, relations=3),
+    # C3 with 10 % of the nodes in a second community (overlapping communities)
+    "c3_overlap": dict(kind="homo_gcn", nodes=1_000_000, edges=20_000_000, features=128, hidden=128, communities=500, overlap=0.1),
     "c3_tenth": dict(kind="homo_gcn", nodes=100_000, edges=2_000_000, features=128, hidden=128, communities=50),
     "c4_small": dict(kind="hetero_sage", nodes=40_000, edges=1_000_000, features=64, hidden=128, communities=40,
                      type_frac=(0.4, 0.25, 0.15, 0.1, 0.1), relations=20),
@@ -71,10 +75,26 @@ class Workload:
         n, e = self.n, self.e
         g = torch.Generator().manual_seed(1234)
         self.type_ptr, self.node_type_names, self.edge_type, self.edge_type_names, self.node_type = [0, n], None, None, None, None
-        if self.kind == "homo_gcn":
+        self.com_of2 = None  # optional second community of a node (overlapping communities)
+        if self.kind == "hetero_gcn1":
+            self.ei = torch.randint(0, n, (2, e), generator=g)
+            self.x = torch.randn(n, self.f, generator=g)
+            self.com_of = torch.randperm(n, generator=g) % self.c
+            self.node_type_names = ["gene"]
+            self.edge_type_names = [("gene", "rel%d" % i, "gene") for i in range(w["relations"])]
+            self.edge_type = torch.arange(e, dtype=torch.int64) % w["relations"]
+            self.node_type = torch.zeros(n, dtype=torch.float32)
+            self.out_type = "gene"
+            self.q_in_type = 17
+            self.queries = [17]
+        elif self.kind == "homo_gcn":
             self.ei = rmat_edges(n, e, g) if w.get("rmat") else torch.randint(0, n, (2, e), generator=g)
             self.x = torch.randn(n, self.f, generator=g)
             self.com_of = torch.randperm(n, generator=g) % self.c  # c disjoint, equal communities
+            if w.get("overlap"):
+                extra = torch.rand(n, generator=g) < w["overlap"]
+                second = torch.randint(0, self.c, (n,), generator=g)
+                self.com_of2 = torch.where(extra, second, torch.full((n,), -1, dtype=torch.int64))
             q0 = 17
             nq = w.get("queries", 1)
             self.queries = [q0] if nq == 1 else torch.randperm(n, generator=g)[:nq].tolist()
@@ -118,6 +138,8 @@ class Workload:
     def model_name(self):
         if self.kind == "homo_gcn":
             return "2xGCNConv(%d)+Linear(%d,1)" % (self.h, self.h)
+        if self.kind == "hetero_gcn1":
+            return "HeteroConv(%d x GCNConv(%d), sum)+MLP(%d-16-32-1)+Sigmoid" % (len(self.edge_type_names), self.h, self.h)
         return "2xHeteroConv(%d x SAGEConv(%d, mean), sum)+Linear(%d,1)+Sigmoid" % (len(self.edge_type_names), self.h, self.h)
 
     def make_model(self, seed=7):
@@ -144,7 +166,13 @@ class Workload:
                     xnn.HeteroConv({r: xnn.SAGEConv((h, h), h) for r in wl.edge_type_names}), nn.ReLU()])
                 self.fc = nn.ModuleList([xnn.Linear(h, 1), nn.Sigmoid()])
 
-        return (GCN2() if self.kind == "homo_gcn" else HeteroSAGE2()).eval()
+        class HeteroGCN1(nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.conv = nn.ModuleList([xnn.HeteroConv({r: xnn.GCNConv(f, h) for r in wl.edge_type_names}), nn.ReLU()])
+                self.fc = nn.ModuleList([xnn.Linear(h, 16), nn.ReLU(), xnn.Linear(16, 32), nn.ReLU(), xnn.Linear(32, 1), nn.Sigmoid()])
+
+        return {"homo_gcn": GCN2, "hetero_sage": HeteroSAGE2, "hetero_gcn1": HeteroGCN1}[self.kind]().eval()
 
     def oracle_model(self, arch):
         """Same weights in the oracle's CPU stand-in layers (for the CPU baseline / parity check)."""
@@ -152,6 +180,8 @@ class Workload:
 
         if self.kind == "homo_gcn":
             m = fm.HomoGCN(self.f, (self.h, self.h), (self.h, 1), final_sigmoid=False)
+        elif self.kind == "hetero_gcn1":
+            m = fm.HeteroGCNSingleType(self.f, self.edge_type_names, conv_dims=(self.h,), head_dims=(self.h, 16, 32, 1))
         else:
             m = fm.HeteroSAGE({t: self.f for t in self.node_type_names}, self.edge_type_names, self.out_type,
                               conv_dims=(self.h, self.h), head_dims=(self.h, 1))
@@ -181,11 +211,11 @@ class Workload:
             g = GraphSpec(self.x.to(dev), self.ei.to(dev), self.type_ptr, self.node_type_names, self.edge_type.to(dev),
                           self.edge_type_names)
         eng = MaskedForward(g, lower(arch), self.queries, prune=False, precision=precision,
-                            zero_edge_rule=self.kind != "homo_gcn")
+                            zero_edge_rule=self.kind == "hetero_sage")  # the zero-edge rule belongs to the multi-node-type branch
         return arch, eng
 
 
-def make_masks(n_rows, n, c, com_of, seed):
+def make_masks(n_rows, n, c, com_of, seed, com_of2=None):
     """Coalition rows of the reference's family: row i perturbs community i mod C internally (iid node
     bits) and switches every other community on/off as a block (antithetic pairs)."""
     g = torch.Generator().manual_seed(seed)
@@ -193,9 +223,13 @@ def make_masks(n_rows, n, c, com_of, seed):
     ext = torch.rand(half, c, generator=g) < 0.5
     ext = torch.cat([ext, ~ext])[:n_rows]
     mask = torch.empty((n_rows, n), dtype=torch.uint8)
+    has2 = None if com_of2 is None else com_of2 >= 0
     for i in range(n_rows):
         row = ext[i][com_of]
         own = com_of == (i % c)
+        if has2 is not None:  # overlapping communities: external activation is an OR over the memberships (masks.py:192),
+            row[has2] |= ext[i][com_of2[has2]]  # internal bits overwrite shared nodes (masks.py:338)
+            own = own | (com_of2 == (i % c))
         row[own] = torch.rand(int(own.sum()), generator=g) < 0.5
         mask[i] = row
     return mask
@@ -251,7 +285,7 @@ def run_reference(args, rank):
     torch.set_num_threads(os.cpu_count())
     om = wl.oracle_model(wl.make_model())
     b = args.ref_coalitions
-    mask = make_masks(b * (args.steps + args.warmup), wl.n, wl.c, wl.com_of, 99).bool().numpy()
+    mask = make_masks(b * (args.steps + args.warmup), wl.n, wl.c, wl.com_of, 99, wl.com_of2).bool().numpy()
     times = []
     for i in range(args.steps + args.warmup):
         t0 = time.perf_counter()
@@ -343,7 +377,7 @@ def main():
     nq = len(wl.queries)
     s_local = args.coalitions_per_gpu
     w = -(-s_local // 32)
-    mask_host = make_masks(s_local, n, c, com_of, 1000 + rank).pin_memory()
+    mask_host = make_masks(s_local, n, c, com_of, 1000 + rank, wl.com_of2).pin_memory()
     mask_dev = torch.empty_like(mask_host, device=dev)
     act = torch.zeros((n, w), dtype=torch.int32, device=dev)
     pop = torch.zeros(s_local, dtype=torch.int32, device=dev)
@@ -379,6 +413,7 @@ def main():
     # ---- timed: resident inputs ----
     lib.xpgnn_profile(1)
     launches0 = _lib.launch_count()
+    stats0 = eng.stats.cpu().clone()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
         barrier()
@@ -392,6 +427,9 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     launches = _lib.launch_count() - launches0
+    active_visits = torch.tensor([float((eng.stats.cpu() - stats0)[1])], device=dev)  # active edge visits of this rank
+    if world > 1:
+        dist.all_reduce(active_visits, op=dist.ReduceOp.SUM)
     prof_ms = (np.zeros(6), np.zeros(6, dtype=np.int64))
     lib.xpgnn_profile_read(prof_ms[0].ctypes.data, prof_ms[1].ctypes.data)
     lib.xpgnn_profile(0)
@@ -457,6 +495,7 @@ def main():
             "config": config_dict(args, wl),
             "coalition_rows_per_s": value / nq,
             "masked_gteps": value / nq * visits / 1e9,
+            "active_gteps": float(active_visits.item()) / (ms_total / 1e3) / 1e9,  # edges that are active in their coalition
             "e2e": {"value": evals / e2e_total, "unit": "coalition evals/s",
                     "h2d_bytes_per_step": int(mask_host.numel()), "d2h_bytes_per_step": int(y_host.numel() * 4)},
             "gpu_launches": int(launches),

@@ -52,6 +52,14 @@ def main():
     from bikg_graph_explainability_public_b200 import nn as xnn
     from pathway_explanations.explainer import Explainer
 
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if world > 1:  # one process per GPU: the coalitions of every query are sharded, one NCCL all-gather of the predictions
+        import torch.distributed as dist
+
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
+
     g = torch.Generator().manual_seed(1234)
     n, e = args.nodes, args.edges
     ei = torch.randint(0, n, (2, e), generator=g) if args.graph == "uniform" else rmat_edges(n, e, g)
@@ -87,10 +95,15 @@ def main():
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         out.append({"query": q, "in_degree": int(indeg[q]), "seconds": dt, **ex.last_stats,
-                    "top_community": None if pdf is None or len(pdf) == 0 else str(pdf.index[0])})
+                    "top_community": None if pdf is None or len(pdf) == 0 else str(pdf.index[0]),
+                    "score_checksum": None if pdf is None else float(pdf["score"].abs().sum()), "rank": rank, "world": world})
         print(json.dumps(out[-1]), flush=True)
-    print(json.dumps({"graph": args.graph, "nodes": n, "edges": e, "communities": args.communities, "names": args.names,
-                      "s_per_explained_query_median": float(np.median([o["seconds"] for o in out]))}))
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    if rank == 0:
+        print(json.dumps({"graph": args.graph, "nodes": n, "edges": e, "communities": args.communities, "names": args.names,
+                          "world": world, "s_per_explained_query_median": float(np.median([o["seconds"] for o in out]))}))
 
 
 if __name__ == "__main__":
