@@ -354,6 +354,45 @@ def test_compact_path_hub_rows(kind, lib, monkeypatch):
 
 
 @pytest.mark.parametrize("kind", ["gcn", "sage"])
+def test_compact_path_without_edges(kind, lib):
+    """Only self loops in the input: GCN drops them (zero edges left, every node is its own unit loop), SAGE keeps
+    them.  Empty coalitions and empty rows through the compaction, the SpMM and the tile table."""
+    from bikg_graph_explainability_public_b200.engine import GraphSpec, MaskedForward
+    from bikg_graph_explainability_public_b200.lowering import lower
+    from oracle import fixture_models as fm
+    from oracle.xpgnn_oracle import kernel_output
+
+    g = torch.Generator().manual_seed(2)
+    n, f, s = 300, 24, 40
+    x = torch.randn(n, f, generator=g)
+    ei = torch.arange(n).repeat(2, 1)
+    arch = (fm.HomoGCN(f, (32, 32), (32, 8, 1), seed=1) if kind == "gcn" else fm.HomoSAGE(f, (32, 32), (32, 1), seed=1)).eval()
+    mask = torch.rand(s, n, generator=g) < 0.5
+    mask[0] = True
+    mask[1] = False
+    q = 11
+    _, y_ref = kernel_output(mask.numpy(), x, ei.numpy(), arch, q)
+    y = MaskedForward(GraphSpec(x.cuda(), ei.cuda(), [0, n]), lower(arch), [q])(_pack(lib, mask), s)[:, 0].cpu().numpy()
+    np.testing.assert_allclose(y, y_ref.numpy().reshape(-1), rtol=Y_RTOL, atol=Y_ATOL)
+
+
+def test_compact_path_is_deterministic(lib):
+    """Dynamic work scheduling and the CTA-level reductions of hub rows add in a fixed order: bitwise equal runs."""
+    from bikg_graph_explainability_public_b200.engine import GraphSpec, MaskedForward
+    from bikg_graph_explainability_public_b200.lowering import lower
+
+    x, ei, arch, mask, q = _random_model_case(4, "gcn", n=5000, e=60000, f=32, hidden=(128, 128), s=64)
+    g = torch.Generator().manual_seed(8)
+    n = x.shape[0]
+    ei = torch.cat([ei, torch.stack([torch.randint(0, n, (4000,), generator=g), torch.full((4000,), q)])], 1)
+    act = _pack(lib, mask)
+    eng = MaskedForward(GraphSpec(x.cuda(), ei.cuda(), [0, n]), lower(arch), [q, 3])
+    y0 = eng(act, 64).cpu().numpy()
+    for _ in range(3):
+        np.testing.assert_array_equal(eng(act, 64).cpu().numpy(), y0)
+
+
+@pytest.mark.parametrize("kind", ["gcn", "sage"])
 def test_bf16_transform_mode_within_tolerance(kind, lib):
     """precision="bf16": dense transforms on tcgen05 with bf16 operands (fp32 accumulate, fp32 storage).
     Bar from BASELINE.json north_star: predictions within 2e-2 relative."""
