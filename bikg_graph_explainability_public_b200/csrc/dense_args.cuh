@@ -38,6 +38,7 @@ struct DenseArgs {
   const float* rs_packed;      // optional row scale per entry: (1 + masked in-degree)^-1/2 (GCN operand of the next layer)
   // ---- bf16 activation storage (tensor-core bf16 mode only): `in` / `out` point at __nv_bfloat16, all strides in elements ----
   int in16, out16;
+  int exp_flags;               // experiments only (XPGNN_DENSE_EXP): 1 skip stores, 2 skip loads, 4 skip MMAs
 };
 constexpr int kPackShift = 26;  // node ids < 2^26 in the packed tile table
 

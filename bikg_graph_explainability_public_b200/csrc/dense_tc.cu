@@ -27,6 +27,8 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__constant__ int g_backoff_after = 16;  // failed polls before a waiting thread starts sleeping (XPGNN_DENSE_BACKOFF)
+
 template <bool BACKOFF = true>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
@@ -40,7 +42,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(addr), "r"(parity)
         : "memory");
     // waiting warps must not eat the issue slots / shared-memory pipe of the working ones
-    if (BACKOFF && !done) __nanosleep(spin < 4 ? 20 : 100);
+    if (BACKOFF && !done && spin >= (uint32_t)g_backoff_after) __nanosleep(32);
     if (spin > (1u << 24)) __trap();  // never hang the GPU: a lost arrival becomes an error
   }
 }
@@ -317,8 +319,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const DenseArgs
         const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-          buf[2 * p] = ld_row[p] ? __ldg(reinterpret_cast<const float4*>(ld_row[p] + o0)) : zero;
-          buf[2 * p + 1] = ld_row[p] ? __ldg(reinterpret_cast<const float4*>(ld_row[p] + o1)) : zero;
+          buf[2 * p] = (ld_row[p] && !(a.exp_flags & 2)) ? __ldg(reinterpret_cast<const float4*>(ld_row[p] + o0)) : zero;
+          buf[2 * p + 1] = (ld_row[p] && !(a.exp_flags & 2)) ? __ldg(reinterpret_cast<const float4*>(ld_row[p] + o1)) : zero;
         }
       }
       if (a.rows_packed && nxt_ti != ti + 1 && ti + 1 < my_tiles) {  // table entries of the next tile, in flight with the data
@@ -390,6 +392,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const DenseArgs
             const uint64_t da_hi = smem_desc(a_hi + a_off, 128, Cfg::K16 * 128);
             const uint64_t db_hi = smem_desc(sB_addr + b_off, 128, kb16 * 128);
             const uint32_t first = (kc == 0 && ks == 0) ? 0u : 1u;
+            if (a.exp_flags & 4) continue;
             umma<MODE>(d_tmem, da_hi, db_hi, idesc, first);
             if (MODE == 0) {
               const uint64_t da_lo = smem_desc(a_lo + a_off, 128, Cfg::K16 * 128);
@@ -492,7 +495,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const DenseArgs
               }
               v[i].x *= rs_r[i]; v[i].y *= rs_r[i]; v[i].z *= rs_r[i]; v[i].w *= rs_r[i];
             }
-            if (a.out16) {
+            if (a.exp_flags & 1) {
+            } else if (a.out16) {
               __nv_bfloat16* out16 = reinterpret_cast<__nv_bfloat16*>(a.out);
 #pragma unroll
               for (int i = 0; i < 4; ++i)
@@ -545,7 +549,13 @@ static bool tc_eligible(const DenseArgs& d, int mode) {
   return tc_stages(d, mode) >= 2;
 }
 
-int launch_dense_tc(const DenseArgs& d, int mode, cudaStream_t st) {
+int launch_dense_tc(const DenseArgs& d_in, int mode, cudaStream_t st) {
+  DenseArgs d = d_in;
+  if (const char* e = getenv("XPGNN_DENSE_EXP")) d.exp_flags = atoi(e);
+  if (const char* e = getenv("XPGNN_DENSE_BACKOFF")) {
+    const int v = atoi(e);
+    XP_CHECK(cudaMemcpyToSymbolAsync(g_backoff_after, &v, sizeof(int), 0, cudaMemcpyHostToDevice, st));
+  }
   XP_REQUIRE(tc_eligible(d, mode), "shape not eligible for the tensor-core dense path");
   const int n_pad = (d.n_out + 15) / 16 * 16;
   uint32_t cols = 32;
