@@ -392,6 +392,44 @@ def test_compact_path_is_deterministic(lib):
         np.testing.assert_array_equal(eng(act, 64).cpu().numpy(), y0)
 
 
+@pytest.mark.parametrize("seed", list(range(8)))
+def test_compact_path_randomized(seed, lib, monkeypatch):
+    """Random configurations (conv kind, depth / widths, hubs, coalition count, tile size, query set): compact path vs
+    the oracle and vs the tile path."""
+    from bikg_graph_explainability_public_b200.engine import GraphSpec, MaskedForward
+    from bikg_graph_explainability_public_b200.lowering import lower
+    from oracle.xpgnn_oracle import kernel_output
+
+    rng = np.random.default_rng(100 + seed)
+    kind = ["gcn", "sage"][seed % 2]
+    hidden = [(64,), (128, 64), (32, 32, 32), (16, 48), (128, 128), (64, 192), (256, 128), (48,)][seed]
+    n = int(rng.integers(300, 3000))
+    e = int(rng.integers(2 * n, 12 * n))
+    s = int(rng.integers(1, 100))
+    x, ei, arch, mask, q = _random_model_case(50 + seed, kind, n=n, e=e, f=int(rng.choice([20, 32, 64])), hidden=hidden, s=max(s, 2))
+    g = torch.Generator().manual_seed(seed)
+    if seed % 3 != 2:  # hub rows above the long-row thresholds
+        for hub, k in ((q, 1500), (int(rng.integers(0, n)), 2600)):
+            ei = torch.cat([ei, torch.stack([torch.randint(0, n, (k,), generator=g), torch.full((k,), hub)])], 1)
+    mask = mask[:max(s, 2)]
+    s = mask.shape[0]
+    mask[rng.integers(0, s)] = torch.rand(n, generator=g) < 0.05   # a sparse coalition
+    queries = [q] + rng.integers(0, n, size=int(rng.integers(0, 3))).tolist()
+    _, y_ref = kernel_output(mask.numpy(), x, ei.numpy(), arch, q)
+    act = _pack(lib, mask)
+    gs = GraphSpec(x.cuda(), ei.cuda(), [0, n])
+    tile = [None, 8, 4, 16][seed % 4]
+    y = MaskedForward(gs, lower(arch), queries, tile_coalitions=tile)(act, s).cpu().numpy()
+    np.testing.assert_allclose(y[:, 0], y_ref.numpy().reshape(-1), rtol=Y_RTOL, atol=Y_ATOL)
+    monkeypatch.setenv("XPGNN_COMPACT", "0")
+    y_tile = MaskedForward(gs, lower(arch), queries)(act, s).cpu().numpy()
+    np.testing.assert_allclose(y_tile, y, rtol=3e-5, atol=1e-6)
+    monkeypatch.delenv("XPGNN_COMPACT")
+    if kind == "gcn" and all(h % 64 == 0 for h in hidden):  # bf16 activation storage where it applies
+        y16 = MaskedForward(gs, lower(arch), queries, precision="bf16_act", tile_coalitions=tile)(act, s).cpu().numpy()
+        np.testing.assert_allclose(y16, y, rtol=2e-2, atol=2e-3)
+
+
 @pytest.mark.parametrize("kind", ["gcn", "sage"])
 def test_bf16_transform_mode_within_tolerance(kind, lib):
     """precision="bf16": dense transforms on tcgen05 with bf16 operands (fp32 accumulate, fp32 storage).
