@@ -50,6 +50,9 @@ WORKLOADS = {
     "c3_tenth": dict(kind="homo_gcn", nodes=100_000, edges=2_000_000, features=128, hidden=128, communities=50),
     "c4_small": dict(kind="hetero_sage", nodes=40_000, edges=1_000_000, features=64, hidden=128, communities=40,
                      type_frac=(0.4, 0.25, 0.15, 0.1, 0.1), relations=20),
+    "c4_tiny": dict(kind="hetero_sage", nodes=3_000, edges=40_000, features=32, hidden=64, communities=12,
+                    type_frac=(0.4, 0.25, 0.15, 0.1, 0.1), relations=9),
+    "c2_wide": dict(kind="hetero_gcn1", nodes=2_500, edges=30_000, features=40, hidden=64, communities=10, relations=3),
     "tiny": dict(kind="homo_gcn", nodes=20_000, edges=400_000, features=32, hidden=32, communities=20),
 }
 

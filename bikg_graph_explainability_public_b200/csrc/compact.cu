@@ -48,13 +48,15 @@ __device__ __forceinline__ int grab_rows(int32_t* counter, int lane) {
 // pass 1: edge-activity words of the coalition word + packed per-(coalition, node) counts
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) compact_degree_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-                                                             const uint32_t* __restrict__ act, int W, int w, int b0, int nb, int N,
+                                                             const uint32_t* __restrict__ act, int W, int w, int b0, int nb, int n_rows,
                                                              uint32_t* __restrict__ ebits, unsigned long long* __restrict__ keys,
                                                              float* __restrict__ scale, int kind, int32_t* __restrict__ counter,
-                                                             int long_threshold) {
+                                                             int long_threshold, int row_lo) {
+  // rows = the destination range [row_lo, row_lo + n_rows) of the relation; keys are indexed by the row's position in it
   const int lane = threadIdx.x & 31;
-  for (int vb = grab_rows(counter, lane); vb < N; vb = grab_rows(counter, lane))
-  for (int v = vb; v < min(N, vb + kRowGrab); ++v) {
+  for (int ib = grab_rows(counter, lane); ib < n_rows; ib = grab_rows(counter, lane))
+  for (int idx = ib; idx < min(n_rows, ib + kRowGrab); ++idx) {
+    const int v = row_lo + idx;
     const int e0 = rowptr[v], e1 = rowptr[v + 1];
     if (long_threshold > 0 && e1 - e0 > long_threshold) continue;  // hub row: compact_degree_long_kernel
     const uint32_t av = act[(int64_t)v * W + w];
@@ -72,15 +74,16 @@ __global__ void __launch_bounds__(256) compact_degree_kernel(const int32_t* __re
     // [N][32] by bit of the word: GCN (1 + masked in-degree)^-1/2, SAGE 1 / max(1, masked in-degree)
     if (scale) scale[(int64_t)v * 32 + lane] = kind == XPGNN_CONV_GCN ? gcn_dinv((uint32_t)cnt) : 1.0f / (float)max(cnt, 1);
     const int t = lane - b0;  // lane = bit of the word, t = slot of the tile
-    if (t >= 0 && t < nb) keys[(int64_t)t * N + v] = ((av >> lane) & 1u) ? ((1ull << kKeyShift) | (unsigned long long)cnt) : 0ull;
+    if (t >= 0 && t < nb) keys[(int64_t)t * n_rows + idx] = ((av >> lane) & 1u) ? ((1ull << kKeyShift) | (unsigned long long)cnt) : 0ull;
   }
 }
 
 // hub rows of pass 1: one CTA per row, the warps take the 32-edge batches round-robin, counts summed through shared memory
 __global__ void __launch_bounds__(256) compact_degree_long_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-                                                                  const uint32_t* __restrict__ act, int W, int w, int b0, int nb, int N,
+                                                                  const uint32_t* __restrict__ act, int W, int w, int b0, int nb, int n_rows,
                                                                   uint32_t* __restrict__ ebits, unsigned long long* __restrict__ keys,
-                                                                  float* __restrict__ scale, int kind, const int32_t* __restrict__ long_rows) {
+                                                                  float* __restrict__ scale, int kind, const int32_t* __restrict__ long_rows,
+                                                                  int row_lo) {
   __shared__ int s_cnt[8][32];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int v = long_rows[blockIdx.x];
@@ -103,7 +106,7 @@ __global__ void __launch_bounds__(256) compact_degree_long_kernel(const int32_t*
   for (int w8 = 1; w8 < 8; ++w8) cnt += s_cnt[w8][lane];
   if (scale) scale[(int64_t)v * 32 + lane] = kind == XPGNN_CONV_GCN ? gcn_dinv((uint32_t)cnt) : 1.0f / (float)max(cnt, 1);
   const int t = lane - b0;
-  if (t >= 0 && t < nb) keys[(int64_t)t * N + v] = ((av >> lane) & 1u) ? ((1ull << kKeyShift) | (unsigned long long)cnt) : 0ull;
+  if (t >= 0 && t < nb) keys[(int64_t)t * n_rows + (v - row_lo)] = ((av >> lane) & 1u) ? ((1ull << kKeyShift) | (unsigned long long)cnt) : 0ull;
 }
 
 // destination rows with more than `threshold` in-edges (a property of the graph: found once per forward call)
@@ -116,7 +119,7 @@ __global__ void __launch_bounds__(256) find_long_rows_kernel(const int32_t* __re
 // pass 2 (after the exclusive scan of the keys): per-coalition list of active rows, compact in-edge
 // offsets, per-source GCN weight of layer 0, per-slot totals
 __global__ void __launch_bounds__(256) compact_finalize_kernel(const unsigned long long* __restrict__ keys,
-                                                               const unsigned long long* __restrict__ scanned, int N,
+                                                               const unsigned long long* __restrict__ scanned, int N, int row_lo,
                                                                int32_t* __restrict__ act_list, uint32_t* __restrict__ rowptr_c,
                                                                float* __restrict__ wgt, int2* __restrict__ slot_info,
                                                                long long* __restrict__ slot_base, int32_t* __restrict__ rows_packed,
@@ -138,9 +141,9 @@ __global__ void __launch_bounds__(256) compact_finalize_kernel(const unsigned lo
   const unsigned long long K = keys[g], S = scanned[g], B = scanned[(int64_t)t * N];
   if (K >> kKeyShift) {
     const int64_t i = (int64_t)((S >> kKeyShift) - (B >> kKeyShift));
-    act_list[(int64_t)t * N + i] = v;
+    act_list[(int64_t)t * N + i] = row_lo + v;  // N = rows of the destination range, v = position in it
     rowptr_c[(int64_t)t * (N + 1) + i] = (uint32_t)((S & kEdgeMask) - (B & kEdgeMask));
-    rows_packed[(int64_t)s_tile0 * 128 + i] = (int32_t)(((uint32_t)t << kPackShift) | (uint32_t)v);
+    rows_packed[(int64_t)s_tile0 * 128 + i] = (int32_t)(((uint32_t)t << kPackShift) | (uint32_t)(row_lo + v));
     rs_packed[(int64_t)s_tile0 * 128 + i] = gcn_dinv((uint32_t)(K & kEdgeMask));
     if (long_cnt > 0 && (K & kEdgeMask) > (unsigned long long)long_cnt)  // hub row of this coalition: cspmm_long_kernel
       long_list[atomicAdd(n_long_list, 1)] = (int32_t)(((uint32_t)t << kPackShift) | (uint32_t)i);
@@ -186,19 +189,22 @@ __global__ void __launch_bounds__(256) compact_tilemap_kernel(const int2* __rest
 __global__ void __launch_bounds__(256) compact_edges_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                                                             const uint32_t* __restrict__ ebits, const uint32_t* __restrict__ act, int W,
                                                             int w, int b0, int nb, int N, const unsigned long long* __restrict__ scanned,
-                                                            int32_t* __restrict__ ccol, int32_t* __restrict__ counter, int long_threshold) {
+                                                            int32_t* __restrict__ ccol, int32_t* __restrict__ counter, int long_threshold,
+                                                            int row_lo) {
+  // N = rows of the destination range [row_lo, row_lo + N)
   const int lane = threadIdx.x & 31;
   const uint32_t tile_mask = nb == 32 ? 0xffffffffu : ((1u << nb) - 1u);
   const uint32_t lt = (1u << lane) - 1u;
-  for (int vb = grab_rows(counter, lane); vb < N; vb = grab_rows(counter, lane))
-  for (int v = vb; v < min(N, vb + kRowGrab); ++v) {
+  for (int ib = grab_rows(counter, lane); ib < N; ib = grab_rows(counter, lane))
+  for (int idx = ib; idx < min(N, ib + kRowGrab); ++idx) {
+    const int v = row_lo + idx;
     const uint32_t av = (act[(int64_t)v * W + w] >> b0) & tile_mask;
     if (!av) continue;
     const int e0 = rowptr[v], e1 = rowptr[v + 1];
     if (e0 == e1) continue;
     if (long_threshold > 0 && e1 - e0 > long_threshold) continue;  // hub row: compact_edges_long_kernel
     unsigned long long base = 0;  // lane t: write cursor of slot t (offset into the concatenated lists)
-    if ((av >> lane) & 1u) base = scanned[(int64_t)lane * N + v] & kEdgeMask;
+    if ((av >> lane) & 1u) base = scanned[(int64_t)lane * N + idx] & kEdgeMask;
     for (int b = e0; b < e1; b += 32) {
       const int e = b + lane;
       int u = -1;
@@ -244,6 +250,10 @@ struct L0RowsArgs {
   const int32_t* long_rows;  // rows with more than long_threshold in-edges (hub rows): one CTA each in the LONG variant
   int long_threshold;        // 0: no splitting
   int32_t* counter;          // row counter of the dynamic schedule (zero at launch)
+  // several relations into one destination type (HeteroConv sum): the first writes, the others add, the last finishes
+  int row_lo, row_hi;        // destination range of the relation (rows outside are skipped)
+  int accumulate;            // 1: add the partial sum already stored in `out`
+  int finish;                // 1: add the bias / addend, apply the activation (and pre-scale); 0: store the partial sum
 };
 
 constexpr int kLongRow = 1024;    // in-edges above which a destination row is processed by a whole CTA
@@ -255,7 +265,7 @@ constexpr int kLongCompact = 256; // active in-edges above which a compact row i
 __global__ void __launch_bounds__(256) compact_edges_long_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                                                                  const uint32_t* __restrict__ ebits, const uint32_t* __restrict__ act, int W,
                                                                  int w, int b0, int nb, int N, const unsigned long long* __restrict__ scanned,
-                                                                 int32_t* __restrict__ ccol, const int32_t* __restrict__ long_rows) {
+                                                                 int32_t* __restrict__ ccol, const int32_t* __restrict__ long_rows, int row_lo) {
   __shared__ int s_cnt[8][32];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint32_t tile_mask = nb == 32 ? 0xffffffffu : ((1u << nb) - 1u);
@@ -277,7 +287,7 @@ __global__ void __launch_bounds__(256) compact_edges_long_kernel(const int32_t* 
   __syncthreads();
   unsigned long long base = 0;
   if ((av >> lane) & 1u) {
-    base = scanned[(int64_t)lane * N + v] & kEdgeMask;
+    base = scanned[(int64_t)lane * N + (v - row_lo)] & kEdgeMask;
     for (int w8 = 0; w8 < wib; ++w8) base += s_cnt[w8][lane];
   }
   for (int b = bs; b < be; b += 32) {
@@ -350,8 +360,9 @@ __global__ void __launch_bounds__(256, 2) l0_rows_kernel(const L0RowsArgs a) {
   const bool gcn = a.kind == XPGNN_CONV_GCN;
   const int ncb = a.h0 / 64;
   const float lower = a.act_fn == XPGNN_ACT_RELU ? 0.0f : -INFINITY;
-  for (int vb = LONG ? 0 : grab_rows(a.counter, lane); vb < a.N; vb = LONG ? a.N : grab_rows(a.counter, lane))
-  for (int v = LONG ? a.long_rows[blockIdx.x] : vb; v < (LONG ? a.N : min(a.N, vb + kRowGrab)); v += LONG ? a.N : 1) {
+  const int n_rows = a.row_hi - a.row_lo;  // destination range of the relation
+  for (int vb = LONG ? 0 : grab_rows(a.counter, lane); vb < n_rows; vb = LONG ? n_rows : grab_rows(a.counter, lane))
+  for (int v = LONG ? a.long_rows[blockIdx.x] : a.row_lo + vb; v < (LONG ? a.N : a.row_lo + min(n_rows, vb + kRowGrab)); v += LONG ? a.N : 1) {
     const uint32_t av = a.act[(int64_t)v * a.W + a.w] & live;
     if (!av) continue;  // LONG: the same row for the whole CTA, so every warp leaves together
     const int n_slots = __popc(av), nq = (n_slots + 3) >> 2;
@@ -439,9 +450,9 @@ __global__ void __launch_bounds__(256, 2) l0_rows_kernel(const L0RowsArgs a) {
       const float* zs = a.z + (int64_t)v * a.h0 + cb * 64 + lane * 2;
       float2 self = make_float2(0.f, 0.f), add = self;
       if (gcn) self = __ldg(reinterpret_cast<const float2*>(zs));
-      if (a.bias) add = __ldg(reinterpret_cast<const float2*>(a.bias + cb * 64 + lane * 2));
+      if (a.bias && a.finish) add = __ldg(reinterpret_cast<const float2*>(a.bias + cb * 64 + lane * 2));
       const int64_t cm_off = (int64_t)(cb * 2 + (lane >> 4)) * a.out_chunk_stride + (int64_t)v * 32 + (lane & 15) * 2;
-      if (a.r0c) {
+      if (a.r0c && a.finish) {
         const float2 r = __ldg(reinterpret_cast<const float2*>(a.r0c + (int64_t)(cb * 2 + (lane >> 4)) * a.r0_chunk_stride + (int64_t)v * 32 + (lane & 15) * 2));
         add.x += r.x; add.y += r.y;
       }
@@ -462,12 +473,18 @@ __global__ void __launch_bounds__(256, 2) l0_rows_kernel(const L0RowsArgs a) {
           float2 o;
           o.x = dv * fmaf(self.x, sw, acc[k].x) + add.x;
           o.y = dv * fmaf(self.y, sw, acc[k].y) + add.y;
-          if (SIGMOID) {
-            o.x = apply_act(o.x, XPGNN_ACT_SIGMOID); o.y = apply_act(o.y, XPGNN_ACT_SIGMOID);
-          } else {
-            o.x = fmaxf(o.x, lower); o.y = fmaxf(o.y, lower);
+          if (!OUT16 && a.accumulate) {  // partial sum of the relations before this one
+            const float2 pr = *reinterpret_cast<const float2*>(outp + (int64_t)b * a.out_s_stride);
+            o.x += pr.x; o.y += pr.y;
           }
-          o.x *= pv; o.y *= pv;
+          if (a.finish) {
+            if (SIGMOID) {
+              o.x = apply_act(o.x, XPGNN_ACT_SIGMOID); o.y = apply_act(o.y, XPGNN_ACT_SIGMOID);
+            } else {
+              o.x = fmaxf(o.x, lower); o.y = fmaxf(o.y, lower);
+            }
+            o.x *= pv; o.y *= pv;
+          }
           if (OUT16) *reinterpret_cast<__nv_bfloat162*>(outp16 + (int64_t)b * a.out_s_stride) = __floats2bfloat162_rn(o.x, o.y);
           else __stcs(reinterpret_cast<float2*>(outp + (int64_t)b * a.out_s_stride), o);
         }
@@ -511,7 +528,8 @@ __device__ __forceinline__ void st_hint4(float* ptr, const float4& v, uint64_t p
 // A row is owned by CW/4 lanes (float4 each); a warp advances 32/(CW/4) rows together.
 // ------------------------------------------------------------------------------------------
 struct CspmmArgs {
-  int nb, N, n_chunks, kind, layer0, act_fn, prescale;
+  int nb, N, n_chunks, kind, layer0, act_fn, prescale;  // layer0: the self term is weighted by deg^-1/2 as well (operand not pre-scaled)
+  int prof_cat;               // -1: by layer0
   const int2* slot_info;
   const int32_t* slot_tile_start;
   const int32_t* act_list;    // [nb][N]
@@ -792,6 +810,8 @@ struct CHeadArgs {
   const float* in;                  // last conv output, chunk-major
   int64_t in_s_stride, in_chunk_stride;
   int dim0, cw, cw_lg, in16;        // in16: bf16 activations in 64-element chunks
+  const float* iso_out;             // hetero: isolated value of the last conv layer per query [n_query][dim0] (precomputed)
+  const unsigned long long* tile_active;  // zero-edge rule (model.py:213-215): active in-edges of the slot over all relations
   const int32_t* query;
   int n_query, out_col;
   float* y;                         // y[slot * n_query + q]
@@ -826,6 +846,9 @@ __global__ void __launch_bounds__(128) compact_head_kernel(const CHeadArgs a, in
       for (int i = threadIdx.x; i < a.dim0; i += blockDim.x) x0[i] = src[(int64_t)(i >> a.cw_lg) * a.in_chunk_stride + (i & (a.cw - 1))];
     }
     __syncthreads();
+  } else if (a.iso_out) {
+    for (int i = threadIdx.x; i < a.dim0; i += blockDim.x) x0[i] = a.iso_out[(int64_t)q * a.dim0 + i];
+    __syncthreads();
   } else {
     for (int i = threadIdx.x; i < a.h0; i += blockDim.x) {
       const int64_t off = (int64_t)(i >> a.cw_lg) * a.z_chunk_stride + (int64_t)qv * a.cw + (i & (a.cw - 1));
@@ -845,7 +868,11 @@ __global__ void __launch_bounds__(128) compact_head_kernel(const CHeadArgs a, in
     __syncthreads();
     float* tp = x0; x0 = x1; x1 = tp;
   }
-  if (threadIdx.x == 0) a.y[(int64_t)slot * a.n_query + q] = x0[a.out_col];
+  if (threadIdx.x == 0) {
+    float r = x0[a.out_col];
+    if (a.tile_active && a.tile_active[slot] == 0ull) r = 0.0f;
+    a.y[(int64_t)slot * a.n_query + q] = r;
+  }
 }
 
 // ------------------------------------------------------------------------------------------ host
@@ -965,7 +992,7 @@ static int launch_cspmm(const CspmmArgs& a, int cw, cudaStream_t st) {
   int per_sm = 0;
   XP_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, 256, 0));
   const int grid = kNumSMs * std::max(per_sm, 1);
-  ProfScope ps(a.layer0 ? PROF_SPMM_INVARIANT : PROF_SPMM_TILE, st);
+  ProfScope ps(a.prof_cat > 0 ? a.prof_cat : (a.layer0 ? PROF_SPMM_INVARIANT : PROF_SPMM_TILE), st);
   XP_LAUNCH(k, grid, 256, 0, st, a);
   if (a.long_cnt > 0) {
     void (*kl)(const CspmmArgs) = cw == 32 ? (a.wgt ? cspmm_long_kernel<32, true> : cspmm_long_kernel<32, false>)
@@ -1037,10 +1064,10 @@ int forward_compact(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32
       {
         ProfScope ps(PROF_SCALE, st);
         XP_LAUNCH(compact_degree_kernel, grid_rows, 256, 0, st, R0.rowptr, R0.col, act, W, w, b0, nb, N, lay.ebits, lay.keys,
-                  l0_rows ? lay.scale : nullptr, kind, lay.counters + 15, n_long > 0 ? kLongRow : 0);
+                  l0_rows ? lay.scale : nullptr, kind, lay.counters + 15, n_long > 0 ? kLongRow : 0, 0);
         if (n_long > 0)
           XP_LAUNCH(compact_degree_long_kernel, n_long, 256, 0, st, R0.rowptr, R0.col, act, W, w, b0, nb, N, lay.ebits, lay.keys,
-                    l0_rows ? lay.scale : nullptr, kind, lay.long_rows);
+                    l0_rows ? lay.scale : nullptr, kind, lay.long_rows, 0);
       }
       {
         ProfScope ps(PROF_COMPACT, st);
@@ -1049,15 +1076,15 @@ int forward_compact(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32
         size_t tmp = lay.cub_bytes;
         XP_CHECK(cub::DeviceScan::ExclusiveSum(lay.cub_tmp, tmp, lay.keys, lay.scanned, (int64_t)nb * N + 1, st));
         g_launches.fetch_add(1, std::memory_order_relaxed);
-        XP_LAUNCH(compact_finalize_kernel, dim3((unsigned)ceil_div(N, 256), (unsigned)nb), 256, 0, st, lay.keys, lay.scanned, N,
+        XP_LAUNCH(compact_finalize_kernel, dim3((unsigned)ceil_div(N, 256), (unsigned)nb), 256, 0, st, lay.keys, lay.scanned, N, 0,
                   lay.act_list, lay.rowptr_c, (kind == XPGNN_CONV_GCN && !l0_rows) ? lay.wgt : nullptr, lay.slot_info, lay.slot_base,
                   lay.rows_packed, lay.rs_packed, n_long > 0 ? kLongCompact : 0, lay.long_list, lay.n_long_list);
         XP_LAUNCH(compact_tilemap_kernel, 1, 256, 0, st, lay.slot_info, nb, lay.slot_tile_start, lay.n_tiles, NL, stats, lay.counters);
         XP_LAUNCH(compact_edges_kernel, grid_rows, 256, 0, st, R0.rowptr, R0.col, lay.ebits, act, W, w, b0, nb, N, lay.scanned, lay.ccol,
-                  lay.counters + 14, n_long > 0 ? kLongRow : 0);
+                  lay.counters + 14, n_long > 0 ? kLongRow : 0, 0);
         if (n_long > 0)
           XP_LAUNCH(compact_edges_long_kernel, n_long, 256, 0, st, R0.rowptr, R0.col, lay.ebits, act, W, w, b0, nb, N, lay.scanned,
-                    lay.ccol, lay.long_rows);
+                    lay.ccol, lay.long_rows, 0);
       }
       float* cur = lay.hbuf[0];
       float* nxt = lay.hbuf[1];
@@ -1084,6 +1111,7 @@ int forward_compact(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32
           ProfScope ps(PROF_SPMM_INVARIANT, st);
           const int grid = (int)std::min<int64_t>(ceil_div(N, 8 * kRowGrab), (int64_t)kNumSMs * 2);
           r.long_rows = lay.long_rows; r.long_threshold = n_long > 0 ? kLongRow : 0; r.counter = lay.counters + 13;
+          r.row_lo = 0; r.row_hi = N; r.accumulate = 0; r.finish = 1;
           const bool sg = L.act == XPGNN_ACT_SIGMOID;
           if (act16) r.out_chunk_stride = cstride16;
           void (*k0)(const L0RowsArgs) = act16 ? (sg ? l0_rows_kernel<true, false, true> : l0_rows_kernel<false, false, true>)
@@ -1173,6 +1201,434 @@ int forward_compact(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32
       {
         ProfScope ps(PROF_HEAD, st);
         XP_LAUNCH(compact_head_kernel, nb * p->n_query, 128, sizeof(float) * 2 * max_dim, st, h, max_dim);
+      }
+    }
+  }
+  return 0;
+}
+
+
+// ==========================================================================================
+// Hetero compact path: HeteroConv(sum) stacks of SAGEConv(mean) / same-type GCNConv relations (BASELINE C4).
+// Every relation is a bipartite graph with its own CSR, masked degrees and per-coalition compacted lists; the
+// relations into one destination type add into the same activation rows (first writes, others add, last
+// finishes).  Same kernels as the homogeneous driver above, which stays the path of single-relation models.
+// ==========================================================================================
+constexpr int kMaxIsoGroups = 8;   // destination groups (node types) per layer in the isolated chain
+constexpr int kMaxIsoSelf = 16;    // layer-0 GCN relations whose Z_r[q] joins the isolated value
+
+struct IsoArgs {
+  int n_layers, h0, act0;
+  const float* r0c;
+  int64_t r0_chunk_stride;
+  int n_self;
+  const float* self_z[kMaxIsoSelf];  // biased row-major Z_r (index by global node id)
+  int self_lo[kMaxIsoSelf], self_hi[kMaxIsoSelf];
+  int n_groups[kMaxConvIso];
+  int g_lo[kMaxConvIso][kMaxIsoGroups], g_hi[kMaxConvIso][kMaxIsoGroups];
+  const float* g_w[kMaxConvIso][kMaxIsoGroups];  // sum over the group of (GCN: lin.weight | SAGE: lin_r.weight), may be NULL
+  const float* g_b[kMaxConvIso][kMaxIsoGroups];  // sum of the biases, may be NULL
+  int h_in[kMaxConvIso], h_out[kMaxConvIso], act[kMaxConvIso];
+  const int32_t* query;
+  float* iso_out;  // [n_query][h_out of the last layer]
+};
+
+// value of a query node in a coalition in which it is inactive (no messages reach it in any layer): coalition invariant
+__global__ void __launch_bounds__(128) hetero_iso_kernel(const IsoArgs a, int max_dim) {
+  extern __shared__ float sm[];
+  float* x0 = sm;
+  float* x1 = sm + max_dim;
+  const int q = blockIdx.x, qv = a.query[q];
+  for (int i = threadIdx.x; i < a.h0; i += blockDim.x) {
+    float r = a.r0c[(int64_t)(i >> 5) * a.r0_chunk_stride + (int64_t)qv * 32 + (i & 31)];
+    for (int k = 0; k < a.n_self; ++k)
+      if (qv >= a.self_lo[k] && qv < a.self_hi[k]) r += a.self_z[k][(int64_t)qv * a.h0 + i];
+    x0[i] = apply_act(r, a.act0);
+  }
+  __syncthreads();
+  int dim = a.h0;
+  for (int l = 1; l < a.n_layers; ++l) {
+    int g = -1;
+    for (int k = 0; k < a.n_groups[l]; ++k)
+      if (qv >= a.g_lo[l][k] && qv < a.g_hi[l][k]) g = k;
+    for (int n = threadIdx.x; n < a.h_out[l]; n += blockDim.x) {
+      float acc = 0.0f;
+      if (g >= 0) {
+        if (a.g_w[l][g]) {
+          const float* wr = a.g_w[l][g] + (int64_t)n * a.h_in[l];
+          for (int k = 0; k < a.h_in[l]; ++k) acc = fmaf(x0[k], __ldg(wr + k), acc);
+        }
+        if (a.g_b[l][g]) acc += __ldg(a.g_b[l][g] + n);
+      }
+      x1[n] = apply_act(acc, a.act[l]);
+    }
+    __syncthreads();
+    float* tp = x0; x0 = x1; x1 = tp;
+    dim = a.h_out[l];
+  }
+  for (int i = threadIdx.x; i < dim; i += blockDim.x) a.iso_out[(int64_t)q * dim + i] = x0[i];
+}
+
+__global__ void compact_add_into_kernel(float* __restrict__ acc, const float* __restrict__ x, int n, int first) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) acc[i] = first ? x[i] : acc[i] + x[i];
+}
+
+__global__ void compact_sum_active_kernel(const int2* __restrict__ slot_info, int nb, unsigned long long* __restrict__ tile_active, int first) {
+  const int t = threadIdx.x;
+  if (t < nb) tile_active[t] = (first ? 0ull : tile_active[t]) + (unsigned long long)slot_info[t].y;
+}
+
+struct HCsr {  // one unique relation CSR and its per-tile compaction
+  const int32_t *rowptr, *col;
+  int kind, lo, hi, n_edges, n_long;
+  uint32_t* ebits;
+  float *scale, *wgt, *rs_packed;
+  int32_t *act_list, *slot_tile_start, *n_tiles, *counters, *long_rows, *n_long_dev, *long_list, *n_long_list, *rows_packed, *ccol;
+  uint32_t* rowptr_c;
+  int2* slot_info;
+  long long* slot_base;
+};
+
+struct HLayout {
+  std::vector<HCsr> csr;
+  std::vector<std::vector<int>> map;       // [layer][relation] -> csr
+  std::vector<float*> zr;                  // layer-0 relations: biased row-major Z_r
+  float* r0c;
+  unsigned long long *keys, *scanned, *tile_active;
+  void* cub_tmp;
+  size_t cub_bytes;
+  std::vector<std::vector<float*>> wroot;  // [layer >= 1][relation]: summed SAGE root weights of its destination group
+  std::vector<std::vector<float*>> iso_w, iso_b;  // [layer >= 1][relation]: merged isolated-chain weights / biases of its group
+  float *iso_out, *hbuf[2], *agg;
+  int64_t bytes;
+};
+
+static bool same_dst(const xpgnn_relation_t& a, const xpgnn_relation_t& b) { return a.dst_lo == b.dst_lo && a.dst_hi == b.dst_hi; }
+
+bool compact_hetero_eligible(const xpgnn_plan_t* p) {
+  if (!compact_enabled() || (getenv("XPGNN_COMPACT_HETERO") && std::string(getenv("XPGNN_COMPACT_HETERO")) == "0")) return false;
+  if (p->prune || p->n_layers < 1 || p->n_layers > kMaxConvIso || p->n_head > kMaxHeadC || p->n_nodes >= (1 << kPackShift)) return false;
+  if (p->precision == 2) return false;  // bf16 storage cannot accumulate relation by relation
+  int n_self = 0;
+  for (int l = 0; l < p->n_layers; ++l) {
+    const xpgnn_layer_t& L = p->layers_host[l];
+    if (L.n_rel < 1 || L.h_out % 64 || L.h_out > 256) return false;
+    if (l > 0 && L.h_in != p->layers_host[l - 1].h_out) return false;
+    int groups = 0;
+    for (int r = 0; r < L.n_rel; ++r) {
+      const xpgnn_relation_t& R = L.rel_host[r];
+      if (R.conv_kind == XPGNN_CONV_GCN && (R.src_lo != R.dst_lo || R.src_hi != R.dst_hi)) return false;
+      if (R.dst_hi <= R.dst_lo || R.src_hi <= R.src_lo) return false;
+      bool first = true;
+      for (int q = 0; q < r; ++q) first = first && !same_dst(L.rel_host[q], R);
+      groups += first;
+      if (l == 0 && R.conv_kind == XPGNN_CONV_GCN) ++n_self;
+    }
+    if (groups > kMaxIsoGroups) return false;
+  }
+  return n_self <= kMaxIsoSelf;
+}
+
+static HLayout hetero_carve(const xpgnn_plan_t* p, void* ws, int64_t cap, int tile) {
+  HLayout h{};
+  Bump b(ws, cap);
+  const int64_t N = p->n_nodes;
+  const int NL = p->n_layers;
+  h.map.resize(NL);
+  for (int l = 0; l < NL; ++l) {
+    const xpgnn_layer_t& L = p->layers_host[l];
+    h.map[l].resize(L.n_rel);
+    for (int r = 0; r < L.n_rel; ++r) {
+      const xpgnn_relation_t& R = L.rel_host[r];
+      int id = -1;
+      for (size_t i = 0; i < h.csr.size(); ++i)
+        if (h.csr[i].rowptr == R.rowptr && h.csr[i].col == R.col && h.csr[i].kind == R.conv_kind) id = (int)i;
+      if (id < 0) {
+        HCsr c{};
+        c.rowptr = R.rowptr; c.col = R.col; c.kind = R.conv_kind; c.lo = R.dst_lo; c.hi = R.dst_hi; c.n_edges = R.n_edges;
+        h.csr.push_back(c);
+        id = (int)h.csr.size() - 1;
+      }
+      h.map[l][r] = id;
+    }
+  }
+  const xpgnn_layer_t& L0 = p->layers_host[0];
+  for (int r = 0; r < L0.n_rel; ++r) {
+    const xpgnn_relation_t& R = L0.rel_host[r];
+    float* z = b.take<float>((int64_t)(R.src_hi - R.src_lo) * L0.h_out);
+    h.zr.push_back(z ? z - (int64_t)R.src_lo * L0.h_out : nullptr);
+  }
+  h.r0c = b.take<float>(N * L0.h_out);
+  int64_t nd_max = 1;
+  for (auto& c : h.csr) nd_max = std::max<int64_t>(nd_max, c.hi - c.lo);
+  h.keys = b.take<unsigned long long>((int64_t)tile * nd_max + 1);
+  h.scanned = b.take<unsigned long long>((int64_t)tile * nd_max + 1);
+  h.cub_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, h.cub_bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (int64_t)tile * nd_max + 1);
+  h.cub_tmp = b.take<char>((int64_t)h.cub_bytes + 256);
+  h.tile_active = b.take<unsigned long long>(32);
+  for (auto& c : h.csr) {
+    const int64_t E = std::max(c.n_edges, 1), nd = c.hi - c.lo;
+    c.ebits = b.take<uint32_t>(E);
+    // everything below is indexed by the position in the destination range; `scale` and `wgt` are read by global node
+    // id (destination row, GCN: source of the same type), so their pointers are biased by the range start
+    float* sc = b.take<float>(nd * 32);
+    c.scale = sc ? sc - (int64_t)c.lo * 32 : nullptr;
+    float* wg = c.kind == XPGNN_CONV_GCN ? b.take<float>((int64_t)tile * nd) : nullptr;
+    c.wgt = wg;
+    c.act_list = b.take<int32_t>((int64_t)tile * nd);
+    c.rowptr_c = b.take<uint32_t>((int64_t)tile * (nd + 1));
+    c.slot_info = b.take<int2>(32);
+    c.slot_base = b.take<long long>(32);
+    c.slot_tile_start = b.take<int32_t>(33);
+    c.n_tiles = b.take<int32_t>(1);
+    c.counters = b.take<int32_t>(16);
+    c.long_rows = b.take<int32_t>(E / kLongRow + 1);
+    c.n_long_dev = b.take<int32_t>(1);
+    c.long_list = b.take<int32_t>((int64_t)tile * (E / kLongCompact + 1));
+    c.n_long_list = b.take<int32_t>(1);
+    c.rows_packed = b.take<int32_t>((int64_t)tile * ceil_div(nd, 128) * 128);
+    c.rs_packed = b.take<float>((int64_t)tile * ceil_div(nd, 128) * 128);
+    c.ccol = b.take<int32_t>((int64_t)tile * E);
+  }
+  h.wroot.resize(NL); h.iso_w.resize(NL); h.iso_b.resize(NL);
+  int hmax = 0;
+  for (int l = 0; l < NL; ++l) {
+    const xpgnn_layer_t& L = p->layers_host[l];
+    hmax = std::max(hmax, L.h_out);
+    if (l == 0) continue;
+    for (int r = 0; r < L.n_rel; ++r) {
+      h.wroot[l].push_back(b.take<float>((int64_t)L.h_out * L.h_in));
+      h.iso_w[l].push_back(b.take<float>((int64_t)L.h_out * L.h_in));
+      h.iso_b[l].push_back(b.take<float>(L.h_out));
+    }
+  }
+  h.iso_out = b.take<float>((int64_t)p->n_query * hmax);
+  h.hbuf[0] = b.take<float>((int64_t)tile * N * hmax);
+  if (NL > 1) {
+    h.hbuf[1] = b.take<float>((int64_t)tile * N * hmax);
+    h.agg = b.take<float>((int64_t)tile * N * hmax);
+  }
+  h.bytes = (b.off + 255) & ~255ll;
+  return h;
+}
+
+int64_t compact_hetero_workspace_bytes(const xpgnn_plan_t* p, int tile) { return hetero_carve(p, nullptr, 0, tile).bytes; }
+
+int forward_compact_hetero(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32_t s0, int32_t n_s, float* y, void* workspace,
+                           int64_t workspace_bytes, int64_t* stats, cudaStream_t st, int dense_prec) {
+  const int N = p->n_nodes, NL = p->n_layers, cw = 32, cw_lg = 5;
+  int tile = 32;
+  while (tile > 1 && hetero_carve(p, nullptr, 0, tile).bytes > workspace_bytes) tile >>= 1;
+  XP_REQUIRE(hetero_carve(p, nullptr, 0, tile).bytes <= workspace_bytes, "workspace too small even for one coalition per tile");
+  HLayout lay = hetero_carve(p, workspace, workspace_bytes, tile);
+  int hmax = 0;
+  for (int l = 0; l < NL; ++l) hmax = std::max(hmax, p->layers_host[l].h_out);
+  const int64_t hstride = (int64_t)N * hmax, cstride = (int64_t)N * cw;
+  const xpgnn_layer_t& L0 = p->layers_host[0];
+  XP_REQUIRE(L0.h_in == p->f_in, "layer 0 input width != feature width");
+  for (auto& c : lay.csr) XP_REQUIRE((int64_t)tile * std::max(c.n_edges, 1) < (1ll << kKeyShift), "tile x edges exceeds the packed scan key");
+
+  // first / last relation into every destination group, per layer
+  std::vector<std::vector<char>> first(NL), last(NL), group_root(NL);
+  for (int l = 0; l < NL; ++l) {
+    const xpgnn_layer_t& L = p->layers_host[l];
+    first[l].assign(L.n_rel, 1); last[l].assign(L.n_rel, 1); group_root[l].assign(L.n_rel, 0);
+    for (int r = 0; r < L.n_rel; ++r)
+      for (int q = 0; q < L.n_rel; ++q)
+        if (q != r && same_dst(L.rel_host[q], L.rel_host[r])) {
+          if (q < r) first[l][r] = 0;
+          if (q > r) last[l][r] = 0;
+        }
+  }
+
+  // ---- coalition-invariant part: Z_r = X W_r^T (row-major), R0 = sum_r (b_r + X W_root,r^T) (chunk-major) ----
+  XP_CHECK(cudaMemsetAsync(lay.r0c, 0, sizeof(float) * (int64_t)N * L0.h_out, st));
+  for (int r = 0; r < L0.n_rel; ++r) {
+    const xpgnn_relation_t& R = L0.rel_host[r];
+    DenseArgs z{};
+    z.in = p->x; z.ld_in = p->f_in; z.k = p->f_in; z.w = R.w_nbr; z.n_out = L0.h_out; z.out = lay.zr[r]; z.ld_out = L0.h_out;
+    z.rows_per_s = R.src_hi - R.src_lo; z.row_lo = R.src_lo; z.M = z.rows_per_s; z.dst_lo = 0; z.dst_hi = N;
+    if (launch_dense(z, st, dense_prec)) return 1;
+    const bool sage_root = R.conv_kind == XPGNN_CONV_SAGE_MEAN && R.w_root;
+    if (sage_root || R.b_nbr) {
+      DenseArgs rt = z;  // k = 0 degenerates to "add the bias"
+      rt.k = sage_root ? p->f_in : 0; rt.w = sage_root ? R.w_root : R.w_nbr; rt.b = R.b_nbr; rt.out = lay.r0c;
+      rt.ld_out = cw; rt.cw_out = cw; rt.cw_out_lg = cw_lg; rt.out_chunk_stride = cstride;
+      rt.rows_per_s = R.dst_hi - R.dst_lo; rt.row_lo = R.dst_lo; rt.M = rt.rows_per_s; rt.accumulate = 1;
+      if (launch_dense(rt, st, dense_prec)) return 1;
+    }
+  }
+  // merged weights: SAGE root transform per destination group, isolated chain per group
+  IsoArgs iso{};
+  iso.n_layers = NL; iso.h0 = L0.h_out; iso.act0 = L0.act; iso.r0c = lay.r0c; iso.r0_chunk_stride = cstride;
+  for (int r = 0; r < L0.n_rel; ++r) {
+    const xpgnn_relation_t& R = L0.rel_host[r];
+    if (R.conv_kind != XPGNN_CONV_GCN) continue;
+    iso.self_z[iso.n_self] = lay.zr[r]; iso.self_lo[iso.n_self] = R.dst_lo; iso.self_hi[iso.n_self] = R.dst_hi;
+    ++iso.n_self;
+  }
+  int max_dim = L0.h_out;
+  for (int l = 1; l < NL; ++l) {
+    const xpgnn_layer_t& L = p->layers_host[l];
+    iso.h_in[l] = L.h_in; iso.h_out[l] = L.h_out; iso.act[l] = L.act;
+    max_dim = std::max(max_dim, std::max(L.h_in, L.h_out));
+    const int nw = L.h_out * L.h_in;
+    for (int r = 0; r < L.n_rel; ++r) {
+      if (!last[l][r]) continue;
+      int n_root = 0, n_w = 0, n_b = 0;
+      for (int q = 0; q <= r; ++q) {
+        const xpgnn_relation_t& Q = L.rel_host[q];
+        if (!same_dst(Q, L.rel_host[r])) continue;
+        const float* wq = Q.conv_kind == XPGNN_CONV_GCN ? Q.w_nbr : Q.w_root;
+        if (Q.conv_kind == XPGNN_CONV_SAGE_MEAN && Q.w_root) {
+          XP_LAUNCH(compact_add_into_kernel, (int)ceil_div(nw, 256), 256, 0, st, lay.wroot[l][r], Q.w_root, nw, n_root == 0);
+          ++n_root;
+        }
+        if (wq) {
+          XP_LAUNCH(compact_add_into_kernel, (int)ceil_div(nw, 256), 256, 0, st, lay.iso_w[l][r], wq, nw, n_w == 0);
+          ++n_w;
+        }
+        if (Q.b_nbr) {
+          XP_LAUNCH(compact_add_into_kernel, (int)ceil_div(L.h_out, 256), 256, 0, st, lay.iso_b[l][r], Q.b_nbr, L.h_out, n_b == 0);
+          ++n_b;
+        }
+      }
+      group_root[l][r] = n_root > 0;
+      const int g = iso.n_groups[l]++;
+      iso.g_lo[l][g] = L.rel_host[r].dst_lo; iso.g_hi[l][g] = L.rel_host[r].dst_hi;
+      iso.g_w[l][g] = n_w ? lay.iso_w[l][r] : nullptr; iso.g_b[l][g] = n_b ? lay.iso_b[l][r] : nullptr;
+    }
+  }
+  iso.query = p->query; iso.iso_out = lay.iso_out;
+  XP_LAUNCH(hetero_iso_kernel, p->n_query, 128, sizeof(float) * 2 * max_dim, st, iso, max_dim);
+
+  // hub rows per relation CSR
+  for (auto& c : lay.csr) {
+    XP_CHECK(cudaMemsetAsync(c.counters, 0, 16 * sizeof(int32_t), st));
+    XP_CHECK(cudaMemsetAsync(c.n_long_dev, 0, sizeof(int32_t), st));
+    XP_LAUNCH(find_long_rows_kernel, (int)ceil_div(N, 256), 256, 0, st, c.rowptr, N, kLongRow, c.long_rows, c.n_long_dev);
+  }
+  {
+    std::vector<int32_t> nl(lay.csr.size());
+    for (size_t i = 0; i < lay.csr.size(); ++i)
+      XP_CHECK(cudaMemcpyAsync(&nl[i], lay.csr[i].n_long_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    XP_CHECK(cudaStreamSynchronize(st));
+    const bool off = getenv("XPGNN_LONG") && std::string(getenv("XPGNN_LONG")) == "0";
+    for (size_t i = 0; i < lay.csr.size(); ++i) lay.csr[i].n_long = off ? 0 : nl[i];
+  }
+
+  const int w_first = s0 / 32, w_last = (s0 + n_s - 1) / 32;
+  for (int w = w_first; w <= w_last; ++w) {
+    const int bits_in_word = std::min(32, s0 + n_s - w * 32);
+    for (int b0 = 0; b0 < bits_in_word; b0 += tile) {
+      const int nb = std::min(tile, bits_in_word - b0);
+      // ---- per-tile compaction of every relation ----
+      for (size_t i = 0; i < lay.csr.size(); ++i) {
+        HCsr& c = lay.csr[i];
+        const int lt = c.n_long > 0 ? kLongRow : 0;
+        const int nd = c.hi - c.lo;  // rows of the destination range: every per-relation structure is indexed by them
+        const int grid_nd = (int)std::min<int64_t>(std::max<int64_t>(ceil_div(nd, 8 * kRowGrab), 1), (int64_t)kNumSMs * 8);
+        {
+          ProfScope ps(PROF_SCALE, st);
+          XP_LAUNCH(compact_degree_kernel, grid_nd, 256, 0, st, c.rowptr, c.col, act, W, w, b0, nb, nd, c.ebits, lay.keys, c.scale,
+                    c.kind, c.counters + 15, lt, c.lo);
+          if (c.n_long > 0)
+            XP_LAUNCH(compact_degree_long_kernel, c.n_long, 256, 0, st, c.rowptr, c.col, act, W, w, b0, nb, nd, c.ebits, lay.keys,
+                      c.scale, c.kind, c.long_rows, c.lo);
+        }
+        ProfScope ps(PROF_COMPACT, st);
+        XP_CHECK(cudaMemsetAsync(lay.keys + (int64_t)nb * nd, 0, sizeof(unsigned long long), st));  // sentinel of the scan
+        XP_CHECK(cudaMemsetAsync(c.n_long_list, 0, sizeof(int32_t), st));
+        size_t tmp = lay.cub_bytes;
+        XP_CHECK(cub::DeviceScan::ExclusiveSum(lay.cub_tmp, tmp, lay.keys, lay.scanned, (int64_t)nb * nd + 1, st));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        XP_LAUNCH(compact_finalize_kernel, dim3((unsigned)ceil_div(nd, 256), (unsigned)nb), 256, 0, st, lay.keys, lay.scanned, nd, c.lo,
+                  c.act_list, c.rowptr_c, c.wgt, c.slot_info, c.slot_base, c.rows_packed, c.rs_packed, lt ? kLongCompact : 0,
+                  c.long_list, c.n_long_list);
+        XP_LAUNCH(compact_tilemap_kernel, 1, 256, 0, st, c.slot_info, nb, c.slot_tile_start, c.n_tiles, NL, i == 0 ? stats : nullptr,
+                  c.counters);
+        XP_LAUNCH(compact_edges_kernel, grid_nd, 256, 0, st, c.rowptr, c.col, c.ebits, act, W, w, b0, nb, nd, lay.scanned, c.ccol,
+                  c.counters + 14, lt, c.lo);
+        if (c.n_long > 0)
+          XP_LAUNCH(compact_edges_long_kernel, c.n_long, 256, 0, st, c.rowptr, c.col, c.ebits, act, W, w, b0, nb, nd, lay.scanned, c.ccol,
+                    c.long_rows, c.lo);
+        XP_LAUNCH(compact_sum_active_kernel, 1, 32, 0, st, c.slot_info, nb, lay.tile_active, i == 0);
+      }
+      float* cur = lay.hbuf[0];
+      float* nxt = lay.hbuf[1];
+      for (int l = 0; l < NL; ++l) {
+        const xpgnn_layer_t& L = p->layers_host[l];
+        for (int r = 0; r < L.n_rel; ++r) {
+          const xpgnn_relation_t& R = L.rel_host[r];
+          HCsr& c = lay.csr[lay.map[l][r]];
+          const bool gcn = R.conv_kind == XPGNN_CONV_GCN;
+          if (l == 0) {
+            L0RowsArgs a{};
+            a.rowptr = c.rowptr; a.col = c.col; a.ebits = c.ebits; a.act = act; a.W = W; a.w = w; a.b0 = b0; a.nb = nb; a.N = N;
+            a.scale = c.scale; a.z = lay.zr[r]; a.h0 = L.h_out; a.r0c = lay.r0c; a.r0_chunk_stride = cstride;
+            a.out = cur; a.out_s_stride = hstride; a.out_chunk_stride = cstride;
+            a.kind = R.conv_kind; a.act_fn = L.act; a.prescale = 0;
+            a.long_rows = c.long_rows; a.long_threshold = c.n_long > 0 ? kLongRow : 0; a.counter = c.counters + 13;
+            a.row_lo = R.dst_lo; a.row_hi = R.dst_hi; a.accumulate = !first[l][r]; a.finish = last[l][r];
+            ProfScope ps(PROF_SPMM_INVARIANT, st);
+            const bool sg = L.act == XPGNN_ACT_SIGMOID;
+            void (*k0)(const L0RowsArgs) = sg ? l0_rows_kernel<true, false, false> : l0_rows_kernel<false, false, false>;
+            XP_CHECK(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, kL0SmemBytes));
+            const int grid = (int)std::min<int64_t>(std::max<int64_t>(ceil_div(R.dst_hi - R.dst_lo, 8 * kRowGrab), 1), (int64_t)kNumSMs * 2);
+            XP_LAUNCH(k0, grid, 256, kL0SmemBytes, st, a);
+            if (c.n_long > 0) {
+              void (*k1)(const L0RowsArgs) = sg ? l0_rows_kernel<true, true, false> : l0_rows_kernel<false, true, false>;
+              XP_CHECK(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, kL0SmemBytes));
+              XP_LAUNCH(k1, c.n_long, 256, kL0SmemBytes, st, a);
+            }
+            // the row counter of this relation's layer-0 launch is used once per tile; compact_tilemap_kernel re-zeroes it
+          } else {
+            CspmmArgs s{};
+            s.nb = nb; s.N = c.hi - c.lo; s.kind = R.conv_kind; s.layer0 = gcn; s.prof_cat = PROF_SPMM_TILE; s.n_chunks = L.h_in / cw;
+            s.slot_info = c.slot_info; s.slot_tile_start = c.slot_tile_start; s.act_list = c.act_list; s.rowptr_c = c.rowptr_c;
+            s.slot_base = c.slot_base; s.ccol = c.ccol;
+            s.in = cur; s.in_s_stride = hstride; s.in_chunk_stride = cstride; s.wgt = gcn ? c.wgt - c.lo : nullptr;  // read by global source id
+            s.out = lay.agg; s.out_s_stride = hstride; s.out_chunk_stride = cstride; s.act_fn = XPGNN_ACT_NONE;
+            s.counter = c.counters + std::min(l, 12); s.l2_stream = 1; s.l2_gather = 0;
+            s.long_cnt = c.n_long > 0 ? kLongCompact : 0; s.long_list = c.long_list; s.n_long_list = c.n_long_list;
+            if (launch_cspmm(s, cw, st)) return 1;
+            const bool root = last[l][r] && group_root[l][r];
+            DenseArgs d{};
+            d.in = lay.agg; d.in_s_stride = hstride; d.ld_in = cw; d.k = L.h_in; d.cw_in = cw; d.cw_in_lg = cw_lg; d.in_chunk_stride = cstride;
+            d.w = R.w_nbr; d.b = R.b_nbr; d.n_out = L.h_out;
+            d.out = nxt; d.out_s_stride = hstride; d.ld_out = cw; d.cw_out = cw; d.cw_out_lg = cw_lg; d.out_chunk_stride = cstride;
+            d.rows_packed = c.rows_packed; d.n_tiles_dev = c.n_tiles;
+            d.rows_per_s = R.dst_hi - R.dst_lo; d.M = (int64_t)nb * ceil_div(R.dst_hi - R.dst_lo, 128) * 128; d.dst_lo = 0; d.dst_hi = N;
+            d.accumulate = !first[l][r]; d.act_fn = (last[l][r] && !root) ? L.act : XPGNN_ACT_NONE;
+            if (launch_dense(d, st, dense_prec)) return 1;
+            if (root) {  // one root transform per destination group, with the summed lin_r weights
+              DenseArgs rt = d;
+              rt.in = cur; rt.w = lay.wroot[l][r]; rt.b = nullptr; rt.accumulate = 1; rt.act_fn = L.act;
+              if (launch_dense(rt, st, dense_prec)) return 1;
+            }
+          }
+        }
+        if (l > 0) std::swap(cur, nxt);
+      }
+      // ---- head on the query rows ----
+      CHeadArgs h{};
+      int hd = p->layers_host[NL - 1].h_out;
+      h.n_iso = 0; h.iso_out = lay.iso_out;
+      h.n_head = p->n_head;
+      for (int i = 0; i < p->n_head; ++i) {
+        h.head[i] = p->head_host[i];
+        hd = std::max(hd, std::max(p->head_host[i].in, p->head_host[i].out));
+      }
+      h.in = cur; h.in_s_stride = hstride; h.in_chunk_stride = cstride; h.dim0 = p->layers_host[NL - 1].h_out; h.cw = cw; h.cw_lg = cw_lg;
+      h.query = p->query; h.n_query = p->n_query; h.out_col = p->out_col;
+      h.y = y + ((int64_t)(w * 32 + b0) - s0) * p->n_query;
+      h.act = act; h.W = W; h.w = w; h.b0 = b0;
+      h.tile_active = p->zero_edge_rule ? lay.tile_active : nullptr;
+      {
+        ProfScope ps(PROF_HEAD, st);
+        XP_LAUNCH(compact_head_kernel, nb * p->n_query, 128, sizeof(float) * 2 * hd, st, h, hd);
       }
     }
   }

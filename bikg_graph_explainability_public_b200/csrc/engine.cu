@@ -512,6 +512,7 @@ int xpgnn_profile_read(double* ms_host, int64_t* launches_host) {
 int64_t xpgnn_forward_workspace_bytes(const xpgnn_plan_t* plan, int32_t tile_coalitions) {
   if (!plan || plan->n_layers < 1 || tile_coalitions < 1 || tile_coalitions > 32) return -1;
   if (compact_eligible(plan)) return compact_workspace_bytes(plan, tile_coalitions);
+  if (compact_hetero_eligible(plan)) return compact_hetero_workspace_bytes(plan, tile_coalitions);
   std::vector<UniqueCsr> uniq;
   std::vector<std::vector<int>> map;
   collect_unique(plan, uniq, map);
@@ -548,6 +549,7 @@ int xpgnn_forward(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32_t
   if (n_s == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   if (compact_eligible(p)) return forward_compact(p, act, W, s0, n_s, y, workspace, workspace_bytes, stats, st, dense_prec);
+  if (compact_hetero_eligible(p)) return forward_compact_hetero(p, act, W, s0, n_s, y, workspace, workspace_bytes, stats, st, dense_prec);
   const int N = p->n_nodes, NL = p->n_layers;
 
   std::vector<UniqueCsr> uniq;

@@ -55,6 +55,10 @@ int launch_dense(const DenseArgs& d, cudaStream_t st, int precision);
 // ---- compact path (compact.cu) ----
 bool compact_eligible(const xpgnn_plan_t* p);
 int64_t compact_workspace_bytes(const xpgnn_plan_t* p, int tile);
+bool compact_hetero_eligible(const xpgnn_plan_t* p);
+int64_t compact_hetero_workspace_bytes(const xpgnn_plan_t* p, int tile);
+int forward_compact_hetero(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32_t s0, int32_t n_s, float* y, void* workspace,
+                           int64_t workspace_bytes, int64_t* stats, cudaStream_t st, int dense_prec);
 int forward_compact(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32_t s0, int32_t n_s, float* y, void* workspace,
                     int64_t workspace_bytes, int64_t* stats, cudaStream_t st, int dense_prec);
 

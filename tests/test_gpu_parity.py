@@ -7,6 +7,7 @@ import copy
 import hashlib
 import json
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -428,6 +429,30 @@ def test_compact_path_randomized(seed, lib, monkeypatch):
     if kind == "gcn" and all(h % 64 == 0 for h in hidden):  # bf16 activation storage where it applies
         y16 = MaskedForward(gs, lower(arch), queries, precision="bf16_act", tile_coalitions=tile)(act, s).cpu().numpy()
         np.testing.assert_allclose(y16, y, rtol=2e-2, atol=2e-3)
+
+
+@pytest.mark.parametrize("name", ["c4_tiny", "c2_wide"])
+def test_hetero_compact_path_matches_oracle(name, lib, monkeypatch):
+    """Hetero compact path (per-relation compaction, relations into one destination type accumulate, merged root
+    transform, isolated chain of typed queries, zero-edge rule) vs the oracle and vs the per-relation tile path."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+
+    wl = bench.Workload(name)
+    s = 70
+    mask = bench.make_masks(s, wl.n, wl.c, wl.com_of, 3).bool()
+    mask[5] = False                      # a coalition without any active edge (zero-edge rule of the multi-type branch)
+    mask[6] = True
+    arch, eng = wl.engine(torch.device("cuda", 0), "fp32")
+    om = wl.oracle_model(arch)
+    y_ref = wl.oracle_eval(om, mask.numpy())
+    act = _pack(lib, mask)
+    y = eng(act, s)[:, 0].cpu().numpy()
+    np.testing.assert_allclose(y, y_ref, rtol=Y_RTOL, atol=Y_ATOL)
+    np.testing.assert_array_equal(eng(act, s, 32, 38)[:, 0].cpu().numpy(), y[32:70])
+    monkeypatch.setenv("XPGNN_COMPACT_HETERO", "0")
+    _, eng_tile = wl.engine(torch.device("cuda", 0), "fp32")
+    np.testing.assert_allclose(eng_tile(act, s)[:, 0].cpu().numpy(), y, rtol=3e-5, atol=1e-6)
 
 
 @pytest.mark.parametrize("kind", ["gcn", "sage"])
