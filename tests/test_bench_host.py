@@ -72,3 +72,22 @@ def test_rmat_generator_is_skewed_and_in_range():
     assert int(ei.min()) >= 0 and int(ei.max()) < (1 << 12)
     indeg = torch.bincount(ei[1], minlength=1 << 12)
     assert int(indeg.max()) > 20 * float(indeg.float().mean())  # hub rows
+
+
+def test_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the oracle port of the reference's CPU path) prints ONE JSON line with the
+    contract keys; it must work without a GPU."""
+    import json
+    import subprocess
+
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "tiny", "--steps", "1",
+                          "--warmup", "0", "--ref-coalitions", "2"], capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "coalition evals/s" and d["unit"] == "coalition evals/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["config"]["workload"] == "tiny"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
