@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(256) compact_edges_long_kernel(const int32_t* 
 }
 
 constexpr int kL0WStride = 36;  // floats per staged weight row (32 + pad: 16-byte aligned, 4-way instead of 32-way store conflicts)
-constexpr int kL0SmemBytes = 8 * 32 * kL0WStride * 4 + 8 * 32 * 64 * 4 + 8 * 32 * 4;
+constexpr int kL0SmemBytes = 8 * 32 * kL0WStride * 4 + 8 * 32 * 64 * 4 + 8 * 32 * 8;  // weights, Z pieces, source ids / row pointers
 
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
@@ -487,6 +487,130 @@ __global__ void __launch_bounds__(256, 2) l0_rows_kernel(const L0RowsArgs a) {
           }
           if (OUT16) *reinterpret_cast<__nv_bfloat162*>(outp16 + (int64_t)b * a.out_s_stride) = __floats2bfloat162_rn(o.x, o.y);
           else __stcs(reinterpret_cast<float2*>(outp + (int64_t)b * a.out_s_stride), o);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// layer 0 of a HeteroConv(sum): all relations into one destination type in ONE pass over its rows.  The warp loops
+// over the incoming relations of its row; the destination-side normalisation of each relation (SAGE 1 / count, GCN
+// deg^-1/2) is folded into the staged weights, GCN's unit self loop is one more staged edge, so every relation adds
+// into the same accumulators and the row is written once (relation by relation it was read-modify-written per relation).
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxL0Rel = 12;
+struct L0Rel {
+  const int32_t* rowptr;
+  const int32_t* col;
+  const uint32_t* ebits;
+  const float* scale;  // [.][32] by bit of the word, indexed by global node id (biased pointer)
+  const float* z;      // [.][h0] row-major Z_r = X W_r^T, indexed by global source id (biased pointer)
+  int kind;
+};
+struct L0MultiArgs {
+  L0Rel rel[kMaxL0Rel];
+  int n_rel;
+  const uint32_t* act;
+  int W, w, b0, nb, h0;
+  const float* r0c;          // sum over the relations of b_r (+ X W_root,r^T), chunk-major
+  int64_t r0_chunk_stride;
+  float* out;
+  int64_t out_s_stride, out_chunk_stride;
+  int act_fn;
+  int32_t* counter;
+  int row_lo, row_hi;
+};
+
+template <bool SIGMOID>
+__global__ void __launch_bounds__(256, 2) l0_multi_kernel(const L0MultiArgs a) {
+  extern __shared__ __align__(16) uint8_t l0_smem[];
+  float(*s_w)[32][kL0WStride] = reinterpret_cast<float(*)[32][kL0WStride]>(l0_smem);
+  float(*s_z)[32][64] = reinterpret_cast<float(*)[32][64]>(l0_smem + 8 * 32 * kL0WStride * 4);
+  const float*(*s_zp)[32] = reinterpret_cast<const float*(*)[32]>(l0_smem + 8 * 32 * kL0WStride * 4 + 8 * 32 * 64 * 4);
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t live = (a.nb == 32 ? 0xffffffffu : ((1u << a.nb) - 1u)) << a.b0;
+  const int ncb = a.h0 / 64, n_rows = a.row_hi - a.row_lo;
+  const float lower = a.act_fn == XPGNN_ACT_RELU ? 0.0f : -INFINITY;
+  for (int vb = grab_rows(a.counter, lane); vb < n_rows; vb = grab_rows(a.counter, lane))
+  for (int v = a.row_lo + vb; v < a.row_lo + min(n_rows, vb + kRowGrab); ++v) {
+    const uint32_t av = a.act[(int64_t)v * a.W + a.w] & live;
+    if (!av) continue;
+    const int n_slots = __popc(av), nq = (n_slots + 3) >> 2;
+    for (int cb = 0; cb < ncb; ++cb) {
+      float2 acc[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) acc[k] = make_float2(0.f, 0.f);
+      for (int ri = 0; ri < a.n_rel; ++ri) {
+        const L0Rel& R = a.rel[ri];
+        const bool gcn = R.kind == XPGNN_CONV_GCN;
+        const int e0 = R.rowptr[v], e1 = R.rowptr[v + 1];
+        const int n_ent = e1 - e0 + (gcn ? 1 : 0);  // GCN: its unit self loop is entry e1 - e0
+        if (n_ent == 0) continue;
+        // destination-side scale of this relation for every bit of the word (same addresses in all lanes: broadcast loads)
+        float4 dq[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) dq[q] = __ldg(reinterpret_cast<const float4*>(R.scale + (int64_t)v * 32 + q * 4));
+        for (int base = 0; base < n_ent; base += 32) {
+          const int n = min(32, n_ent - base);
+          __syncwarp();
+          if (lane < n) {
+            const int ent = base + lane;
+            const bool self = ent == e1 - e0;  // only for GCN
+            const int u = self ? v : __ldg(R.col + e0 + ent);
+            const uint32_t bits = self ? av : (__ldg(R.ebits + e0 + ent) & av);
+            s_zp[wib][lane] = R.z + (int64_t)u * a.h0;
+            float* wrow = &s_w[wib][lane][0];
+            float4 wq[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              wq[q] = gcn ? __ldg(reinterpret_cast<const float4*>(R.scale + (int64_t)u * 32 + q * 4)) : make_float4(1.f, 1.f, 1.f, 1.f);
+              wq[q].x = (bits >> (4 * q + 0)) & 1u ? wq[q].x * dq[q].x : 0.0f;
+              wq[q].y = (bits >> (4 * q + 1)) & 1u ? wq[q].y * dq[q].y : 0.0f;
+              wq[q].z = (bits >> (4 * q + 2)) & 1u ? wq[q].z * dq[q].z : 0.0f;
+              wq[q].w = (bits >> (4 * q + 3)) & 1u ? wq[q].w * dq[q].w : 0.0f;
+              *reinterpret_cast<float4*>(wrow + 4 * q) = wq[q];
+            }
+            int k = 0;  // in place: position k <- bit b_k of the destination's active slots
+            for (uint32_t m = av; m; m &= m - 1, ++k) wrow[k] = wrow[__ffs(m) - 1];
+            for (; k < 4 * nq; ++k) wrow[k] = 0.0f;
+          }
+          __syncwarp();
+#pragma unroll 4
+          for (int j = 0; j < n; ++j) cp_async8(&s_z[wib][j][lane * 2], s_zp[wib][j] + cb * 64 + lane * 2);
+          cp_async_wait_all();
+          __syncwarp();
+          const float* wr = &s_w[wib][0][0];
+          const float* zr = &s_z[wib][0][0];
+          switch (nq) {
+            case 1: l0_fma<1>(wr, zr, n, lane, acc); break;
+            case 2: l0_fma<2>(wr, zr, n, lane, acc); break;
+            case 3: l0_fma<3>(wr, zr, n, lane, acc); break;
+            case 4: l0_fma<4>(wr, zr, n, lane, acc); break;
+            case 5: l0_fma<5>(wr, zr, n, lane, acc); break;
+            case 6: l0_fma<6>(wr, zr, n, lane, acc); break;
+            case 7: l0_fma<7>(wr, zr, n, lane, acc); break;
+            default: l0_fma<8>(wr, zr, n, lane, acc); break;
+          }
+        }
+      }
+      // ---- epilogue: every normalisation is already inside the weights ----
+      const int64_t cm_off = (int64_t)(cb * 2 + (lane >> 4)) * a.out_chunk_stride + (int64_t)v * 32 + (lane & 15) * 2;
+      const float2 add = __ldg(reinterpret_cast<const float2*>(a.r0c + (int64_t)(cb * 2 + (lane >> 4)) * a.r0_chunk_stride + (int64_t)v * 32 + (lane & 15) * 2));
+      float* outp = a.out + cm_off - (int64_t)a.b0 * a.out_s_stride;
+      uint32_t m = av;
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        if (k < n_slots) {  // warp uniform
+          const int b = __ffs(m) - 1;
+          m &= m - 1;
+          float2 o = make_float2(acc[k].x + add.x, acc[k].y + add.y);
+          if (SIGMOID) {
+            o.x = apply_act(o.x, XPGNN_ACT_SIGMOID); o.y = apply_act(o.y, XPGNN_ACT_SIGMOID);
+          } else {
+            o.x = fmaxf(o.x, lower); o.y = fmaxf(o.y, lower);
+          }
+          __stcs(reinterpret_cast<float2*>(outp + (int64_t)b * a.out_s_stride), o);
         }
       }
     }
@@ -1560,6 +1684,38 @@ int forward_compact_hetero(const xpgnn_plan_t* p, const uint32_t* act, int32_t W
       float* nxt = lay.hbuf[1];
       for (int l = 0; l < NL; ++l) {
         const xpgnn_layer_t& L = p->layers_host[l];
+        // layer 0, one pass per destination type over all of its incoming relations (no hub rows, <= kMaxL0Rel relations)
+        bool multi_l0 = l == 0 && !(getenv("XPGNN_L0_MULTI") && std::string(getenv("XPGNN_L0_MULTI")) == "0");
+        if (multi_l0) {
+          for (auto& c : lay.csr) multi_l0 = multi_l0 && c.n_long == 0;
+          for (int r = 0; r < L.n_rel && multi_l0; ++r) {
+            int members = 0;
+            for (int q = 0; q < L.n_rel; ++q) members += same_dst(L.rel_host[q], L.rel_host[r]);
+            multi_l0 = members <= kMaxL0Rel;
+          }
+        }
+        if (multi_l0) {
+          for (int r = 0; r < L.n_rel; ++r) {
+            if (!first[l][r]) continue;
+            const xpgnn_relation_t& R = L.rel_host[r];
+            L0MultiArgs a{};
+            for (int q = r; q < L.n_rel; ++q) {
+              if (!same_dst(L.rel_host[q], R)) continue;
+              const HCsr& cq = lay.csr[lay.map[l][q]];
+              L0Rel& x = a.rel[a.n_rel++];
+              x.rowptr = cq.rowptr; x.col = cq.col; x.ebits = cq.ebits; x.scale = cq.scale; x.z = lay.zr[q]; x.kind = L.rel_host[q].conv_kind;
+            }
+            a.act = act; a.W = W; a.w = w; a.b0 = b0; a.nb = nb; a.h0 = L.h_out; a.r0c = lay.r0c; a.r0_chunk_stride = cstride;
+            a.out = cur; a.out_s_stride = hstride; a.out_chunk_stride = cstride; a.act_fn = L.act;
+            a.counter = lay.csr[lay.map[l][r]].counters + 13; a.row_lo = R.dst_lo; a.row_hi = R.dst_hi;
+            ProfScope ps(PROF_SPMM_INVARIANT, st);
+            void (*km)(const L0MultiArgs) = L.act == XPGNN_ACT_SIGMOID ? l0_multi_kernel<true> : l0_multi_kernel<false>;
+            XP_CHECK(cudaFuncSetAttribute(km, cudaFuncAttributeMaxDynamicSharedMemorySize, kL0SmemBytes));
+            const int grid = (int)std::min<int64_t>(std::max<int64_t>(ceil_div(R.dst_hi - R.dst_lo, 8 * kRowGrab), 1), (int64_t)kNumSMs * 2);
+            XP_LAUNCH(km, grid, 256, kL0SmemBytes, st, a);
+          }
+          continue;
+        }
         for (int r = 0; r < L.n_rel; ++r) {
           const xpgnn_relation_t& R = L.rel_host[r];
           HCsr& c = lay.csr[lay.map[l][r]];
