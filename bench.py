@@ -53,6 +53,7 @@ WORKLOADS = {
     "c4_tiny": dict(kind="hetero_sage", nodes=3_000, edges=40_000, features=32, hidden=64, communities=12,
                     type_frac=(0.4, 0.25, 0.15, 0.1, 0.1), relations=9),
     "c2_wide": dict(kind="hetero_gcn1", nodes=2_500, edges=30_000, features=40, hidden=64, communities=10, relations=3),
+    "c2_wide2": dict(kind="hetero_gcn1", nodes=2_500, edges=30_000, features=40, hidden=64, communities=10, relations=3, conv_layers=2),
     "tiny": dict(kind="homo_gcn", nodes=20_000, edges=400_000, features=32, hidden=32, communities=20),
 }
 
@@ -90,6 +91,7 @@ class Workload:
             self.out_type = "gene"
             self.q_in_type = 17
             self.queries = [17]
+            self.conv_layers = w.get("conv_layers", 1)
         elif self.kind == "homo_gcn":
             self.ei = rmat_edges(n, e, g) if w.get("rmat") else torch.randint(0, n, (2, e), generator=g)
             self.x = torch.randn(n, self.f, generator=g)
@@ -172,7 +174,10 @@ class Workload:
         class HeteroGCN1(nn.Module):
             def __init__(self):
                 super().__init__()
-                self.conv = nn.ModuleList([xnn.HeteroConv({r: xnn.GCNConv(f, h) for r in wl.edge_type_names}), nn.ReLU()])
+                mods = []
+                for li in range(wl.conv_layers):
+                    mods += [xnn.HeteroConv({r: xnn.GCNConv(f if li == 0 else h, h) for r in wl.edge_type_names}), nn.ReLU()]
+                self.conv = nn.ModuleList(mods)
                 self.fc = nn.ModuleList([xnn.Linear(h, 16), nn.ReLU(), xnn.Linear(16, 32), nn.ReLU(), xnn.Linear(32, 1), nn.Sigmoid()])
 
         return {"homo_gcn": GCN2, "hetero_sage": HeteroSAGE2, "hetero_gcn1": HeteroGCN1}[self.kind]().eval()
@@ -184,7 +189,8 @@ class Workload:
         if self.kind == "homo_gcn":
             m = fm.HomoGCN(self.f, (self.h, self.h), (self.h, 1), final_sigmoid=False)
         elif self.kind == "hetero_gcn1":
-            m = fm.HeteroGCNSingleType(self.f, self.edge_type_names, conv_dims=(self.h,), head_dims=(self.h, 16, 32, 1))
+            m = fm.HeteroGCNSingleType(self.f, self.edge_type_names, conv_dims=(self.h,) * self.conv_layers,
+                                       head_dims=(self.h, 16, 32, 1))
         else:
             m = fm.HeteroSAGE({t: self.f for t in self.node_type_names}, self.edge_type_names, self.out_type,
                               conv_dims=(self.h, self.h), head_dims=(self.h, 1))

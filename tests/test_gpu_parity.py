@@ -431,7 +431,7 @@ def test_compact_path_randomized(seed, lib, monkeypatch):
         np.testing.assert_allclose(y16, y, rtol=2e-2, atol=2e-3)
 
 
-@pytest.mark.parametrize("name", ["c4_tiny", "c2_wide"])
+@pytest.mark.parametrize("name", ["c4_tiny", "c2_wide", "c2_wide2"])
 def test_hetero_compact_path_matches_oracle(name, lib, monkeypatch):
     """Hetero compact path (per-relation compaction, relations into one destination type accumulate, merged root
     transform, isolated chain of typed queries, zero-edge rule) vs the oracle and vs the per-relation tile path."""
