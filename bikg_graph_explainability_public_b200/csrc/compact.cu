@@ -837,6 +837,123 @@ __global__ void __launch_bounds__(256) cspmm_long_kernel(const CspmmArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// layers >= 1 of a HeteroConv(sum), transform-first: Z_r = H W_r^T has been computed per relation over the active
+// rows of its source type; this kernel gathers, per destination row, over the compacted lists of ALL relations into
+// the destination type, adds the merged root term and bias, applies the activation and writes the row ONCE
+// (aggregate-first wrote an aggregate per relation and read-modify-wrote the output per relation).
+// ------------------------------------------------------------------------------------------
+struct MRel {
+  const uint32_t* rowptr_c;    // [nb][nd + 1] compact in-edge offsets of this relation (nd = rows of the destination range)
+  const long long* slot_base;
+  const int32_t* ccol;
+  const float* z;              // transformed sources, chunk-major, indexed by global source id (biased pointer)
+  int64_t z_s_stride, z_chunk_stride;
+  const float* wgt;            // GCN: [nb][.] per-source deg^-1/2, indexed by global source id (biased pointer) | NULL
+  int kind;
+};
+struct CspmmMultiArgs {
+  MRel rel[kMaxL0Rel];
+  int n_rel, nb, nd, n_chunks, act_fn;
+  const int2* slot_info;       // of the destination type (identical for all of its relations)
+  const int32_t* slot_tile_start;
+  const int32_t* act_list;     // [nb][nd]
+  const float* zroot;          // merged root term H Wsum^T, chunk-major, indexed by global destination id (biased) | NULL
+  int64_t zr_s_stride, zr_chunk_stride;
+  const float* bias;           // sum of the relation biases | NULL
+  float* out;
+  int64_t out_s_stride, out_chunk_stride;
+  int32_t* counter;
+};
+
+__global__ void __launch_bounds__(256, 4) cspmm_multi_kernel(const CspmmMultiArgs a) {
+  constexpr int CW = 32, G = 8;
+  __shared__ int s_start[33];
+  __shared__ int s_item;
+  if (threadIdx.x <= a.nb) s_start[threadIdx.x] = a.slot_tile_start[threadIdx.x];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane & 7, grp = lane >> 3;
+  const int total = s_start[a.nb] * a.n_chunks;
+  const uint64_t pol_s = l2_policy(1), pol_g = l2_policy(0);
+  int t = 0;
+  while (true) {
+    if (threadIdx.x == 0) s_item = atomicAdd(a.counter, 1);
+    __syncthreads();
+    const int idx = s_item;
+    __syncthreads();
+    if (idx >= total) break;
+    while (idx >= s_start[t + 1] * a.n_chunks) ++t;
+    const int ntb = s_start[t + 1] - s_start[t];
+    const int rem = idx - s_start[t] * a.n_chunks;
+    const int c = rem / ntb, tb = rem - c * ntb;
+    const int n_act = a.slot_info[t].x;
+    const int32_t* al = a.act_list + (int64_t)t * a.nd;
+    float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.bias) bias = __ldg(reinterpret_cast<const float4*>(a.bias + c * CW + sub * 4));
+#pragma unroll 1
+    for (int it = 0; it < 4; ++it) {
+      const int i = tb * 128 + it * 32 + warp * 4 + grp;
+      const bool valid = i < n_act;
+      const int v = valid ? ld_hint(al + i, pol_s) : 0;
+      float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int ri = 0; ri < a.n_rel; ++ri) {
+        const MRel& R = a.rel[ri];
+        const uint32_t* rp = R.rowptr_c + (int64_t)t * (a.nd + 1);
+        uint32_t e0 = 0, cnt = 0;
+        if (valid) {
+          e0 = ld_hint(rp + i, pol_s);
+          cnt = ld_hint(rp + i + 1, pol_s) - e0;
+        }
+        const uint32_t maxcnt = __reduce_max_sync(0xffffffffu, cnt);
+        const bool gcn = R.kind == XPGNN_CONV_GCN;
+        if (maxcnt == 0 && !gcn) continue;  // warp uniform
+        const int32_t* cc = R.ccol + R.slot_base[t];
+        const float* z_c = R.z + (int64_t)t * R.z_s_stride + (int64_t)c * R.z_chunk_stride + sub * 4;
+        const float* wg = R.wgt ? R.wgt + (int64_t)t * a.nd : nullptr;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (uint32_t base = 0; base < maxcnt; base += G) {
+          int my = -1;
+          float myw = 1.0f;
+          if (base + sub < cnt) {
+            my = ld_hint(cc + e0 + base + sub, pol_s);
+            if (wg) myw = __ldg(wg + my);
+          }
+#pragma unroll
+          for (int j = 0; j < G; ++j) {
+            const int u = __shfl_sync(0xffffffffu, my, grp * G + j);
+            const float wj = __shfl_sync(0xffffffffu, myw, grp * G + j);
+            if (u >= 0) {
+              const float4 x = ld_hint4(z_c + (int64_t)u * CW, pol_g);
+              acc.x = fmaf(wj, x.x, acc.x); acc.y = fmaf(wj, x.y, acc.y);
+              acc.z = fmaf(wj, x.z, acc.z); acc.w = fmaf(wj, x.w, acc.w);
+            }
+          }
+        }
+        if (!valid) continue;
+        if (gcn) {  // dinv_v (sum_u dinv_u Z[u] + dinv_v Z[v])
+          const float dinv = gcn_dinv(cnt);
+          const float4 self = ld_hint4(z_c + (int64_t)v * CW, pol_g);
+          tot.x += dinv * fmaf(dinv, self.x, acc.x); tot.y += dinv * fmaf(dinv, self.y, acc.y);
+          tot.z += dinv * fmaf(dinv, self.z, acc.z); tot.w += dinv * fmaf(dinv, self.w, acc.w);
+        } else {
+          const float inv = 1.0f / (float)max(cnt, 1u);
+          tot.x = fmaf(inv, acc.x, tot.x); tot.y = fmaf(inv, acc.y, tot.y);
+          tot.z = fmaf(inv, acc.z, tot.z); tot.w = fmaf(inv, acc.w, tot.w);
+        }
+      }
+      if (!valid) continue;
+      tot.x += bias.x; tot.y += bias.y; tot.z += bias.z; tot.w += bias.w;
+      if (a.zroot) {
+        const float4 r = ld_hint4(a.zroot + (int64_t)t * a.zr_s_stride + (int64_t)c * a.zr_chunk_stride + (int64_t)v * CW + sub * 4, pol_s);
+        tot.x += r.x; tot.y += r.y; tot.z += r.z; tot.w += r.w;
+      }
+      tot.x = apply_act(tot.x, a.act_fn); tot.y = apply_act(tot.y, a.act_fn);
+      tot.z = apply_act(tot.z, a.act_fn); tot.w = apply_act(tot.w, a.act_fn);
+      st_hint4(a.out + (int64_t)t * a.out_s_stride + (int64_t)c * a.out_chunk_stride + (int64_t)v * CW + sub * 4, tot, pol_s);
+    }
+  }
+}
+
 // bf16 activation storage: the same list-driven pass over 64-element (128-byte) chunks of bf16 rows; 8 lanes x 8
 // elements per row, fp32 accumulation, aggregate written back as bf16 (layers >= 1 only: no weights, addend or activation).
 __device__ __forceinline__ void add_bf16x8(const uint4& q, float (&acc)[8]) {
@@ -1532,7 +1649,19 @@ static HLayout hetero_carve(const xpgnn_plan_t* p, void* ws, int64_t cap, int ti
   h.hbuf[0] = b.take<float>((int64_t)tile * N * hmax);
   if (NL > 1) {
     h.hbuf[1] = b.take<float>((int64_t)tile * N * hmax);
-    h.agg = b.take<float>((int64_t)tile * N * hmax);
+    // aggregate buffer of the relation-by-relation path == pool of the transformed sources Z_r of one destination group
+    // (transform-first path): the larger of the two
+    int64_t pool = (int64_t)tile * N * hmax;
+    for (int l = 1; l < NL; ++l) {
+      const xpgnn_layer_t& L = p->layers_host[l];
+      for (int r = 0; r < L.n_rel; ++r) {
+        int64_t need = (int64_t)tile * (L.rel_host[r].dst_hi - L.rel_host[r].dst_lo) * L.h_out;  // merged root term
+        for (int q = 0; q < L.n_rel; ++q)
+          if (same_dst(L.rel_host[q], L.rel_host[r])) need += (int64_t)tile * (L.rel_host[q].src_hi - L.rel_host[q].src_lo) * L.h_out;
+        pool = std::max(pool, need);
+      }
+    }
+    h.agg = b.take<float>(pool);
   }
   h.bytes = (b.off + 255) & ~255ll;
   return h;
@@ -1555,10 +1684,10 @@ int forward_compact_hetero(const xpgnn_plan_t* p, const uint32_t* act, int32_t W
   for (auto& c : lay.csr) XP_REQUIRE((int64_t)tile * std::max(c.n_edges, 1) < (1ll << kKeyShift), "tile x edges exceeds the packed scan key");
 
   // first / last relation into every destination group, per layer
-  std::vector<std::vector<char>> first(NL), last(NL), group_root(NL);
+  std::vector<std::vector<char>> first(NL), last(NL), group_root(NL), group_bias(NL);
   for (int l = 0; l < NL; ++l) {
     const xpgnn_layer_t& L = p->layers_host[l];
-    first[l].assign(L.n_rel, 1); last[l].assign(L.n_rel, 1); group_root[l].assign(L.n_rel, 0);
+    first[l].assign(L.n_rel, 1); last[l].assign(L.n_rel, 1); group_root[l].assign(L.n_rel, 0); group_bias[l].assign(L.n_rel, 0);
     for (int r = 0; r < L.n_rel; ++r)
       for (int q = 0; q < L.n_rel; ++q)
         if (q != r && same_dst(L.rel_host[q], L.rel_host[r])) {
@@ -1620,6 +1749,7 @@ int forward_compact_hetero(const xpgnn_plan_t* p, const uint32_t* act, int32_t W
         }
       }
       group_root[l][r] = n_root > 0;
+      group_bias[l][r] = n_b > 0;
       const int g = iso.n_groups[l]++;
       iso.g_lo[l][g] = L.rel_host[r].dst_lo; iso.g_hi[l][g] = L.rel_host[r].dst_hi;
       iso.g_w[l][g] = n_w ? lay.iso_w[l][r] : nullptr; iso.g_b[l][g] = n_b ? lay.iso_b[l][r] : nullptr;
@@ -1714,6 +1844,75 @@ int forward_compact_hetero(const xpgnn_plan_t* p, const uint32_t* act, int32_t W
             const int grid = (int)std::min<int64_t>(std::max<int64_t>(ceil_div(R.dst_hi - R.dst_lo, 8 * kRowGrab), 1), (int64_t)kNumSMs * 2);
             XP_LAUNCH(km, grid, 256, kL0SmemBytes, st, a);
           }
+          continue;
+        }
+        // layers >= 1 transform-first: Z_q = H W_q^T per relation over the active rows of its source type, then one gather
+        // pass per destination type over all of its relations (no hub rows, <= kMaxL0Rel relations per type)
+        bool multi_l1 = l > 0 && getenv("XPGNN_L1_MULTI") && std::string(getenv("XPGNN_L1_MULTI")) == "1";  // opt-in: measured slower on C4 (200 vs 224 evals/s)
+        if (multi_l1) {
+          for (auto& c : lay.csr) multi_l1 = multi_l1 && c.n_long == 0;
+          for (int r = 0; r < L.n_rel && multi_l1; ++r) {
+            int members = 0;
+            for (int q = 0; q < L.n_rel; ++q) members += same_dst(L.rel_host[q], L.rel_host[r]);
+            multi_l1 = members <= kMaxL0Rel;
+          }
+        }
+        if (multi_l1) {
+          auto type_csr = [&](int lo, int hi) {  // a relation whose destination range is this node type: its tile table lists the type's active rows
+            for (size_t i = 0; i < lay.csr.size(); ++i)
+              if (lay.csr[i].lo == lo && lay.csr[i].hi == hi) return (int)i;
+            return -1;
+          };
+          for (int r = 0; r < L.n_rel; ++r) {
+            if (!first[l][r]) continue;
+            const xpgnn_relation_t& R = L.rel_host[r];
+            const HCsr& cd = lay.csr[lay.map[l][r]];
+            const int nd = cd.hi - cd.lo;
+            int r_last = r;
+            for (int q = r; q < L.n_rel; ++q)
+              if (same_dst(L.rel_host[q], R)) r_last = q;
+            float* pool = lay.agg;
+            CspmmMultiArgs m{};
+            DenseArgs d{};
+            d.in = cur; d.in_s_stride = hstride; d.ld_in = cw; d.k = L.h_in; d.cw_in = cw; d.cw_in_lg = cw_lg; d.in_chunk_stride = cstride;
+            d.n_out = L.h_out; d.ld_out = cw; d.cw_out = cw; d.cw_out_lg = cw_lg; d.dst_lo = 0; d.dst_hi = N; d.act_fn = XPGNN_ACT_NONE;
+            for (int q = r; q < L.n_rel; ++q) {
+              const xpgnn_relation_t& Q = L.rel_host[q];
+              if (!same_dst(Q, R)) continue;
+              const HCsr& cq = lay.csr[lay.map[l][q]];
+              const int ts = type_csr(Q.src_lo, Q.src_hi);
+              if (ts < 0) continue;  // the source type never receives messages: it has no rows in layers >= 1
+              const int ns = Q.src_hi - Q.src_lo;
+              float* zq = pool;
+              pool += (int64_t)nb * ns * L.h_out;
+              DenseArgs dz = d;
+              dz.w = Q.w_nbr; dz.b = nullptr; dz.out = zq - (int64_t)Q.src_lo * cw; dz.out_s_stride = (int64_t)ns * L.h_out;
+              dz.out_chunk_stride = (int64_t)ns * cw; dz.rows_packed = lay.csr[ts].rows_packed; dz.n_tiles_dev = lay.csr[ts].n_tiles;
+              dz.rows_per_s = ns; dz.M = (int64_t)nb * ceil_div(ns, 128) * 128;
+              if (launch_dense(dz, st, dense_prec)) return 1;
+              MRel& x = m.rel[m.n_rel++];
+              x.rowptr_c = cq.rowptr_c; x.slot_base = cq.slot_base; x.ccol = cq.ccol; x.z = dz.out; x.z_s_stride = dz.out_s_stride;
+              x.z_chunk_stride = dz.out_chunk_stride; x.kind = Q.conv_kind;
+              x.wgt = Q.conv_kind == XPGNN_CONV_GCN ? cq.wgt - cq.lo : nullptr;
+            }
+            if (group_root[l][r_last]) {  // merged root term of the destination type
+              DenseArgs dr = d;
+              dr.w = lay.wroot[l][r_last]; dr.b = nullptr; dr.out = pool - (int64_t)cd.lo * cw; dr.out_s_stride = (int64_t)nd * L.h_out;
+              dr.out_chunk_stride = (int64_t)nd * cw; dr.rows_packed = cd.rows_packed; dr.n_tiles_dev = cd.n_tiles;
+              dr.rows_per_s = nd; dr.M = (int64_t)nb * ceil_div(nd, 128) * 128;
+              if (launch_dense(dr, st, dense_prec)) return 1;
+              m.zroot = dr.out; m.zr_s_stride = dr.out_s_stride; m.zr_chunk_stride = dr.out_chunk_stride;
+            }
+            m.nb = nb; m.nd = nd; m.n_chunks = L.h_out / cw; m.act_fn = L.act;
+            m.slot_info = cd.slot_info; m.slot_tile_start = cd.slot_tile_start; m.act_list = cd.act_list;
+            m.bias = group_bias[l][r_last] ? lay.iso_b[l][r_last] : nullptr;
+            m.out = nxt; m.out_s_stride = hstride; m.out_chunk_stride = cstride; m.counter = lay.csr[lay.map[l][r]].counters + std::min(l, 12);
+            ProfScope ps(PROF_SPMM_TILE, st);
+            int per_sm = 0;
+            XP_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cspmm_multi_kernel, 256, 0));
+            XP_LAUNCH(cspmm_multi_kernel, kNumSMs * std::max(per_sm, 1), 256, 0, st, m);
+          }
+          std::swap(cur, nxt);
           continue;
         }
         for (int r = 0; r < L.n_rel; ++r) {

@@ -450,6 +450,8 @@ def test_hetero_compact_path_matches_oracle(name, lib, monkeypatch):
     y = eng(act, s)[:, 0].cpu().numpy()
     np.testing.assert_allclose(y, y_ref, rtol=Y_RTOL, atol=Y_ATOL)
     np.testing.assert_array_equal(eng(act, s, 32, 38)[:, 0].cpu().numpy(), y[32:70])
+    monkeypatch.setenv("XPGNN_L1_MULTI", "0")   # layers >= 1 aggregate-first relation by relation instead of transform-first per type
+    np.testing.assert_allclose(eng(act, s)[:, 0].cpu().numpy(), y, rtol=3e-5, atol=1e-6)
     monkeypatch.setenv("XPGNN_L0_MULTI", "0")   # layer 0 relation by relation (accumulate / finish) instead of one pass per type
     np.testing.assert_allclose(eng(act, s)[:, 0].cpu().numpy(), y, rtol=3e-5, atol=1e-6)
     monkeypatch.setenv("XPGNN_COMPACT_HETERO", "0")
