@@ -578,6 +578,7 @@ __device__ __forceinline__ void ws_mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void ws_cp_async_arrive(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(ws_u32(bar)) : "memory");
 }
+template <int SLEEP_NS>
 __device__ __forceinline__ void ws_mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = ws_u32(bar);
   uint32_t done = 0;
@@ -589,19 +590,21 @@ __device__ __forceinline__ void ws_mbar_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(done)
         : "r"(addr), "r"(parity)
         : "memory");
-    if (!done) __nanosleep(64);       // a waiting warp must not eat the issue slots of the three working ones
+    if (!done) __nanosleep(SLEEP_NS);  // a waiting warp must not eat the issue slots of the three working ones
     if (spin > (1u << 22)) __trap();  // never hang the GPU: a lost arrival becomes an error
   }
 }
+template <int SLEEP_NS>
 __device__ __forceinline__ void ws_mbar_wait_timed(uint64_t* bar, uint32_t parity, bool timed, unsigned long long& acc) {
   if (timed) {
     const long long t0 = clock64();
-    ws_mbar_wait(bar, parity);
+    ws_mbar_wait<SLEEP_NS>(bar, parity);
     acc += (unsigned long long)(clock64() - t0);
   } else {
-    ws_mbar_wait(bar, parity);
+    ws_mbar_wait<SLEEP_NS>(bar, parity);
   }
 }
+constexpr int kWsProducerSleep = 256, kWsConsumerSleep = 32;  // ns between polls: the producers run ahead, the consumers are the critical path
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {  // through L1: neighbouring 16-byte pieces share a sector
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(ws_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
@@ -724,20 +727,20 @@ __global__ void __launch_bounds__(2 * kWsPairs * 32, 1) l0_ws_kernel(const L0Row
     uint32_t bits_n = 0;
     bool raw_n = false;  // the next row's raw scale rows are on their way into its weight buffer
     if (v_n >= 0) {
-      av_n = a.act[(int64_t)v_n * a.W + a.w] & live;
+      av_n = a.act[(int64_t)v_n * a.W + a.w];
       e0_n = a.rowptr[v_n]; e1_n = a.rowptr[v_n + 1];
       if (lane < e1_n - e0_n) { u_n = __ldg(a.col + e0_n + lane); bits_n = __ldg(a.ebits + e0_n + lane); }
     }
     while (v_n >= 0) {
       const int v = v_n, e0 = e0_n, e1 = e1_n;
-      const uint32_t av = av_n;
+      const uint32_t av = av_n & live;
       const bool raw = raw_n;
       int u = u_n;
       const uint32_t bits0 = bits_n & av;
       v_n = next_v();
       raw_n = false;
-      if (v_n >= 0) {  // in flight while this row is staged
-        av_n = a.act[(int64_t)v_n * a.W + a.w] & live;
+      if (v_n >= 0) {  // in flight while this row is staged (consumed by the prefetch steps / the next iteration only)
+        av_n = a.act[(int64_t)v_n * a.W + a.w];
         e0_n = a.rowptr[v_n]; e1_n = a.rowptr[v_n + 1];
       }
       const bool skip = !av || (a.long_threshold > 0 && e1 - e0 > a.long_threshold);  // nothing active / hub row (LONG launch)
@@ -752,9 +755,9 @@ __global__ void __launch_bounds__(2 * kWsPairs * 32, 1) l0_ws_kernel(const L0Row
         if (pre_step == 0) {
           u_n = 0; bits_n = 0;
           if (lane < e1_n - e0_n) { u_n = __ldg(a.col + e0_n + lane); bits_n = __ldg(a.ebits + e0_n + lane); }
-        } else if (gcn && av_n && !(a.long_threshold > 0 && e1_n - e0_n > a.long_threshold)) {
+        } else if (gcn && (av_n & live) && !(a.long_threshold > 0 && e1_n - e0_n > a.long_threshold)) {
           const int wb = ws_next & 1;
-          ws_mbar_wait_timed(&P.wempty[wb], ((ws_next >> 1) & 1) ^ 1, timed, t_wait0);
+          ws_mbar_wait_timed<kWsProducerSleep>(&P.wempty[wb], ((ws_next >> 1) & 1) ^ 1, timed, t_wait0);
           if (lane < e1_n - e0_n) {
             float* wrow = &P.wb[wb].w[lane][0];
             const float* src = a.scale + (int64_t)u_n * 32;
@@ -785,7 +788,7 @@ __global__ void __launch_bounds__(2 * kWsPairs * 32, 1) l0_ws_kernel(const L0Row
               cp_async_wait0();
               if (lane < n) l0_finish_weights(&T.w[lane][0], bits0, av, nq);
             } else {
-              ws_mbar_wait_timed(&P.wempty[wbuf], ((ws >> 1) & 1) ^ 1, timed, t_wait0);
+              ws_mbar_wait_timed<kWsProducerSleep>(&P.wempty[wbuf], ((ws >> 1) & 1) ^ 1, timed, t_wait0);
               if (lane < n) {
                 uint32_t bits = bits0;
                 if (!first) {  // beyond the prefetched first batch
@@ -803,7 +806,7 @@ __global__ void __launch_bounds__(2 * kWsPairs * 32, 1) l0_ws_kernel(const L0Row
             ++ws;
           }
           const int stage = zs & 1;
-          ws_mbar_wait_timed(&P.zempty[stage], ((zs >> 1) & 1) ^ 1, timed, t_wait1);
+          ws_mbar_wait_timed<kWsProducerSleep>(&P.zempty[stage], ((zs >> 1) & 1) ^ 1, timed, t_wait1);
           // Z pieces: 16 lanes x 16 bytes per in-edge, two in-edges per instruction (coalesced 256-byte requests)
           {
             const int uo = u * a.h0;  // element offset of the lane's own source row (N * h0 < 2^31: checked on the host)
@@ -836,7 +839,7 @@ __global__ void __launch_bounds__(2 * kWsPairs * 32, 1) l0_ws_kernel(const L0Row
       while (pre_step < 2 && v_n >= 0) prefetch_next(ws);
     }
     const int stage = zs & 1;  // end marker
-    ws_mbar_wait(&P.zempty[stage], ((zs >> 1) & 1) ^ 1);
+    ws_mbar_wait<kWsProducerSleep>(&P.zempty[stage], ((zs >> 1) & 1) ^ 1);
     if (lane == 0) P.hdr[stage].flags = WS_END;
     ws_cp_async_arrive(&P.zfull[stage]);
     __syncwarp();
@@ -852,7 +855,7 @@ __global__ void __launch_bounds__(2 * kWsPairs * 32, 1) l0_ws_kernel(const L0Row
     for (int k = 0; k < 32; ++k) acc[k] = make_float2(0.f, 0.f);
     for (uint32_t zs = 0;; ++zs) {
       const int stage = zs & 1;
-      ws_mbar_wait_timed(&P.zfull[stage], (zs >> 1) & 1, timed, t_wait0);
+      ws_mbar_wait_timed<kWsConsumerSleep>(&P.zfull[stage], (zs >> 1) & 1, timed, t_wait0);
       const WsHdr h = P.hdr[stage];
       if (h.flags & WS_END) {
         if (timed && lane == 0) {
@@ -860,8 +863,14 @@ __global__ void __launch_bounds__(2 * kWsPairs * 32, 1) l0_ws_kernel(const L0Row
         }
         break;
       }
-      float2 self = make_float2(0.f, 0.f), add = self;
-      if (h.flags & WS_LAST) l0_epilogue_operands(a, h.v, h.cb, lane, gcn, self, add);  // in flight during the FMAs
+      // epilogue operands: loads only, in flight during the FMAs (nothing may consume them before the loop)
+      float2 self = make_float2(0.f, 0.f), add = self, root = self;
+      if (h.flags & WS_LAST) {
+        if (gcn) self = __ldg(reinterpret_cast<const float2*>(a.z + (int64_t)h.v * a.h0 + h.cb * 64 + lane * 2));
+        if (a.bias && (PLAIN || a.finish)) add = __ldg(reinterpret_cast<const float2*>(a.bias + h.cb * 64 + lane * 2));
+        if (a.r0c && (PLAIN || a.finish))
+          root = __ldg(reinterpret_cast<const float2*>(a.r0c + (int64_t)(h.cb * 2 + (lane >> 4)) * a.r0_chunk_stride + (int64_t)h.v * 32 + (lane & 15) * 2));
+      }
       if (h.flags & WS_FIRST) {
 #pragma unroll
         for (int k = 0; k < 32; ++k) acc[k] = make_float2(0.f, 0.f);
@@ -873,7 +882,10 @@ __global__ void __launch_bounds__(2 * kWsPairs * 32, 1) l0_ws_kernel(const L0Row
       if (timed) t_fma += (unsigned long long)(clock64() - t_f0);
       __syncwarp();
       if (lane == 0) ws_mbar_arrive(&P.zempty[stage]);  // before the epilogue: the next stage's pieces fly during it
-      if (h.flags & WS_LAST) l0_epilogue_tab<SIGMOID, OUT16, PLAIN>(a, T, h.v, n_slots, h.cb, lane, gcn1, pre1, lower, acc, self, add);
+      if (h.flags & WS_LAST) {
+        add.x += root.x; add.y += root.y;
+        l0_epilogue_tab<SIGMOID, OUT16, PLAIN>(a, T, h.v, n_slots, h.cb, lane, gcn1, pre1, lower, acc, self, add);
+      }
       if (h.flags & WS_FREE_W) {
         __syncwarp();
         if (lane == 0) ws_mbar_arrive(&P.wempty[h.wbuf]);
