@@ -613,6 +613,7 @@ __device__ __forceinline__ void cp_async16_cg(void* smem_dst, const void* gmem_s
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 // weight rows whose 32 raw scales already sit in shared memory (cp.async one row ahead): mask, compact in place
 __device__ __forceinline__ void l0_finish_weights(float* wrow, uint32_t bits, uint32_t av, int nq) {
   float4 wq[8];
@@ -885,6 +886,332 @@ __global__ void __launch_bounds__(2 * kWsPairs * 32, 1) l0_ws_kernel(const L0Row
       if (h.flags & WS_LAST) {
         add.x += root.x; add.y += root.y;
         l0_epilogue_tab<SIGMOID, OUT16, PLAIN>(a, T, h.v, n_slots, h.cb, lane, gcn1, pre1, lower, acc, self, add);
+      }
+      if (h.flags & WS_FREE_W) {
+        __syncwarp();
+        if (lane == 0) ws_mbar_arrive(&P.wempty[h.wbuf]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// layer 0, warp specialised, slot x column tiling (widths % 128 == 0).  The kernel above is bound by the shared-memory
+// pipe (68 % busy): with a lane owning 2 columns x all active slots, every in-edge costs 2 x (4 broadcast LDS.128 of
+// weights + 1 LDS.64 of Z) = 20 wavefronts.  Here a consumer lane (g, c) = (lane / 16, lane % 16) owns 8 columns
+// {4c..4c+3, 64+4c..64+4c+3} x 8 of the 16 slots of a SLOT block (slot pairs g, g+2, g+4, g+6 of the block, so that few
+// active slots still spread over both half warps): 2 LDS.128 of Z + NP <= 4 LDS.64 of weights + 8 NP FFMA2 per in-edge
+// for all 128 columns -- 8 wavefronts.  A destination with <= 16 active slots is ONE pass over its in-edges (the usual
+// case: about half of the 32 slots are active), otherwise two.  Stages hold 16 in-edges x 512 bytes.
+// ------------------------------------------------------------------------------------------
+constexpr int kW2EB = 16;  // in-edges per stage
+struct W2Hdr {
+  int v;
+  uint32_t av;
+  int n, cs, sb, wbuf, flags, pad;
+};
+struct W2W {
+  float w[kW2EB][kL0WStride];     // weight rows of a batch, compacted to the destination's active slots
+  long long off[32];              // k-th active slot -> byte offset of its activation tile
+  float dv[32];                   // k-th active slot -> destination scale
+};
+struct W2Pair {
+  float z[2][kW2EB][128];         // Z rows (one 128-column super block) of a stage
+  W2W wb[4];                      // four: the next row's raw scales land in one while this row's batches use theirs
+  W2Hdr hdr[2];
+  uint64_t zfull[2], zempty[2], wempty[4];
+};
+constexpr int kW2SmemBytes = kWsPairs * (int)sizeof(W2Pair);
+static_assert(kW2SmemBytes <= 227 * 1024, "ring does not fit shared memory");
+static_assert(sizeof(W2Pair) % 16 == 0 && sizeof(W2W) % 16 == 0, "cp.async destinations must stay 16-byte aligned");
+
+// acc[p * 8 + i] = (slot pair 2p + g of the block) x column i of the lane (i < 4: 4c + i, else 64 + 4c + i - 4)
+template <int NP>
+__device__ __forceinline__ void ws2_fma(const float* __restrict__ w_rows, const float* __restrict__ z_rows, int n, float2 (&acc)[32]) {
+#pragma unroll(NP <= 2 ? 2 : 1)
+  for (int j = 0; j < n; ++j) {
+    const float4 z0 = *reinterpret_cast<const float4*>(z_rows + j * 128), z1 = *reinterpret_cast<const float4*>(z_rows + j * 128 + 64);
+    const float zs[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      const float2 wp = *reinterpret_cast<const float2*>(w_rows + j * kL0WStride + 4 * p);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ffma2(acc[p * 8 + i], wp, make_float2(zs[i], zs[i]));
+    }
+  }
+}
+__device__ __forceinline__ void ws2_fma_switch(int np, const float* wr, const float* zr, int n, float2 (&acc)[32]) {
+  switch (np) {
+    case 1: ws2_fma<1>(wr, zr, n, acc); break;
+    case 2: ws2_fma<2>(wr, zr, n, acc); break;
+    case 3: ws2_fma<3>(wr, zr, n, acc); break;
+    default: ws2_fma<4>(wr, zr, n, acc); break;
+  }
+}
+
+template <bool SIGMOID, bool OUT16, bool PLAIN>
+__device__ __forceinline__ void ws2_epilogue(const L0RowsArgs& a, const W2W& T, int v, int n_slots, int cs, int sb, int lane, float gcn1, float pre1,
+                                             float lower, const float2 (&acc)[32], const float4 (&ex)[2], const float4 (&add)[2]) {
+  const int g = lane >> 4, c = lane & 15;
+  char* outp[2];
+#pragma unroll
+  for (int b = 0; b < 2; ++b)
+    outp[b] = OUT16 ? reinterpret_cast<char*>(reinterpret_cast<__nv_bfloat16*>(a.out) + (int64_t)(cs * 2 + b) * a.out_chunk_stride + (int64_t)v * 64 + 4 * c -
+                                              (int64_t)a.b0 * a.out_s_stride)
+                    : reinterpret_cast<char*>(a.out + (int64_t)(cs * 4 + b * 2 + (c >> 3)) * a.out_chunk_stride + (int64_t)v * 32 + ((4 * c) & 31) -
+                                              (int64_t)a.b0 * a.out_s_stride);
+  const int np = (min(16, n_slots - 16 * sb) + 3) >> 2;
+  const float pre0 = 1.0f - pre1;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    if (p < np) {  // warp uniform
+      const int k0 = 16 * sb + 4 * p + 2 * g;
+      const float2 dv2 = *reinterpret_cast<const float2*>(&T.dv[k0]);
+      const longlong2 off2 = *reinterpret_cast<const longlong2*>(&T.off[k0]);
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float dv = e ? dv2.y : dv2.x;
+        const long long off = e ? off2.y : off2.x;
+        const bool on = k0 + e < n_slots;
+        const float sw = dv * gcn1, pv = fmaf(dv, pre1, pre0);  // gcn ? dv : 0, prescale ? dv : 1 (exact)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          const float se[4] = {ex[b].x, ex[b].y, ex[b].z, ex[b].w}, ad[4] = {add[b].x, add[b].y, add[b].z, add[b].w};
+          float o[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float2 ap = acc[p * 8 + b * 4 + t];
+            o[t] = dv * fmaf(se[t], sw, e ? ap.y : ap.x) + ad[t];
+          }
+          char* dst = outp[b] + off;
+          if (!PLAIN && !OUT16 && a.accumulate && on) {  // partial sum of the relations before this one
+            const float4 pr = *reinterpret_cast<const float4*>(dst);
+            o[0] += pr.x; o[1] += pr.y; o[2] += pr.z; o[3] += pr.w;
+          }
+          if (PLAIN || a.finish) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              o[t] = SIGMOID ? apply_act(o[t], XPGNN_ACT_SIGMOID) : fmaxf(o[t], lower);
+              o[t] *= pv;
+            }
+          }
+          if (on) {
+            if (OUT16) {
+              __nv_bfloat162 h01 = __floats2bfloat162_rn(o[0], o[1]), h23 = __floats2bfloat162_rn(o[2], o[3]);
+              uint2 pk;
+              pk.x = *reinterpret_cast<uint32_t*>(&h01); pk.y = *reinterpret_cast<uint32_t*>(&h23);
+              *reinterpret_cast<uint2*>(dst) = pk;
+            } else {
+              __stcs(reinterpret_cast<float4*>(dst), make_float4(o[0], o[1], o[2], o[3]));
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+template <bool SIGMOID, bool OUT16, bool PLAIN>
+__global__ void __launch_bounds__(2 * kWsPairs * 32, 1) l0_ws2_kernel(const L0RowsArgs a) {
+  extern __shared__ __align__(128) uint8_t ws_smem[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const bool producer = wid < kWsPairs;
+  W2Pair& P = reinterpret_cast<W2Pair*>(ws_smem)[producer ? wid : wid - kWsPairs];
+  if (producer && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      ws_mbar_init(&P.zfull[i], 33);  // 32 cp.async completions (one per producer lane) + the header / weights arrival
+      ws_mbar_init(&P.zempty[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) ws_mbar_init(&P.wempty[i], 1);
+  }
+  __syncthreads();
+  const uint32_t live = (a.nb == 32 ? 0xffffffffu : ((1u << a.nb) - 1u)) << a.b0;  // bits of the word in this tile
+  const bool gcn = a.kind == XPGNN_CONV_GCN;
+  const int ncs = a.h0 / 128;
+  const bool timed = a.dbg != nullptr && blockIdx.x == 0 && (wid == 0 || wid == kWsPairs);
+  unsigned long long t_wait0 = 0, t_wait1 = 0, t_fma = 0;
+  const long long t_start = timed ? clock64() : 0;
+  if (producer) {
+    const int n_rows = a.row_hi - a.row_lo;
+    uint32_t zs = 0, ws = 0;  // stages / weight buffers handed over so far
+    int g_lo = 0, g_hi = 0;
+    auto next_v = [&]() -> int {
+      if (g_lo >= g_hi) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(a.counter, kWsGrab);
+        g_lo = __shfl_sync(0xffffffffu, base, 0);
+        g_hi = min(n_rows, g_lo + kWsGrab);
+        if (g_lo >= n_rows) return -1;
+      }
+      return a.row_lo + g_lo++;
+    };
+    const int elt = OUT16 ? 2 : 4;  // bytes per stored activation element
+    // Software pipeline over the rows, one step per iteration, so that no load is consumed in the iteration that issues it:
+    //   M (row t+3) active word + row pointers -> E (row t+2) first 16 (source, edge-activity) pairs -> S (row t+1) raw scale
+    //   rows of those sources by cp.async into the weight buffer the row will use + the row's own scales -> P (row t) staging.
+    int m_v = -1, m_e0 = 0, m_e1 = 0;            uint32_t m_act = 0;
+    int e_v = -1, e_e0 = 0, e_e1 = 0, e_u = 0;   uint32_t e_act = 0, e_bits = 0;
+    int s_v = -1, s_e0 = 0, s_e1 = 0, s_u = 0;   uint32_t s_act = 0, s_bits = 0;  bool s_raw = false;  float s_sc = 0.0f;
+    bool more = true;
+    for (int drain = 0; drain < 3;) {
+      // ---- shift ----
+      const int v = s_v, e0 = s_e0, e1 = s_e1;
+      int u = s_u;
+      const uint32_t av = s_act & live, bits0 = s_bits & av;
+      const bool raw = s_raw;
+      const float sc_v = s_sc;
+      s_v = e_v; s_e0 = e_e0; s_e1 = e_e1; s_u = e_u; s_act = e_act; s_bits = e_bits; s_raw = false;
+      e_v = m_v; e_e0 = m_e0; e_e1 = m_e1; e_act = m_act;
+      // ---- M: row t+3 ----
+      m_v = more ? next_v() : -1;
+      if (m_v < 0) { more = false; ++drain; }
+      else {
+        m_act = a.act[(int64_t)m_v * a.W + a.w];
+        m_e0 = a.rowptr[m_v]; m_e1 = a.rowptr[m_v + 1];
+      }
+      // ---- E: row t+2 (its pointers were loaded one iteration ago) ----
+      e_u = 0; e_bits = 0;
+      if (e_v >= 0 && lane < min(kW2EB, e_e1 - e_e0)) { e_u = __ldg(a.col + e_e0 + lane); e_bits = __ldg(a.ebits + e_e0 + lane); }
+      // ---- this row ----
+      const bool valid = v >= 0 && av && !(a.long_threshold > 0 && e1 - e0 > a.long_threshold);  // else: nothing active / hub row (LONG launch)
+      const int n_slots = __popc(av), nq = (n_slots + 3) >> 2, nsb = n_slots > 16 ? 2 : 1;
+      const bool short_row = e1 - e0 <= kW2EB;
+      const int nbuf = !valid ? 0 : (short_row ? 1 : ((e1 - e0 + kW2EB - 1) / kW2EB) * ncs * nsb);  // weight buffers this row takes
+      // ---- S: row t+1 (its sources were loaded one iteration ago) ----
+      const bool s_valid = s_v >= 0 && (s_act & live) && !(a.long_threshold > 0 && s_e1 - s_e0 > a.long_threshold);
+      if (s_valid) s_sc = a.scale[(int64_t)s_v * 32 + lane];
+      auto stage_raw = [&](uint32_t ws_next) {  // raw scale rows of row t+1's first batch into the buffer it will use
+        const int wb = ws_next & 3;
+        ws_mbar_wait_timed<kWsProducerSleep>(&P.wempty[wb], ((ws_next >> 2) & 1) ^ 1, timed, t_wait0);
+        if (lane < min(kW2EB, s_e1 - s_e0)) {
+          float* wrow = &P.wb[wb].w[lane][0];
+          const float* src = a.scale + (int64_t)s_u * 32;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) cp_async16(wrow + 4 * q, src + 4 * q);
+        }
+        cp_async_commit();
+        s_raw = true;
+      };
+      // early unless the buffer it needs is one this row still has to fill (4 buffers; use k waits for the release of use k - 4)
+      const bool early = gcn && s_valid && nbuf < 4;
+      if (early) stage_raw(ws + nbuf);
+      if (valid) {
+        int wbuf = 0;
+        for (int cs = 0; cs < ncs; ++cs)
+        for (int sb = 0; sb < nsb; ++sb) {
+          const bool last_pass = cs == ncs - 1 && sb == nsb - 1;
+          int base = e0;
+          do {  // a row without in-edges still gets one (empty) stage per pass: self loop / bias / root term
+            const int n = max(0, min(kW2EB, e1 - base));
+            const bool first = base == e0 && cs == 0 && sb == 0;
+            const bool stage_w = first || !short_row;  // weights of the batch (kept across the passes of a short row)
+            if (stage_w) {
+              wbuf = ws & 3;
+              W2W& T = P.wb[wbuf];
+              if (first && raw) {  // acquired and filled one iteration ago; the group issued just now may stay in flight
+                if (early) cp_async_wait1(); else cp_async_wait0();
+                if (lane < n) l0_finish_weights(&T.w[lane][0], bits0, av, nq);
+              } else {
+                ws_mbar_wait_timed<kWsProducerSleep>(&P.wempty[wbuf], ((ws >> 2) & 1) ^ 1, timed, t_wait0);
+                if (lane < n) {
+                  uint32_t bits = bits0;
+                  if (!first) {  // beyond the prefetched first batch
+                    u = __ldg(a.col + base + lane);
+                    bits = __ldg(a.ebits + base + lane) & av;
+                  }
+                  l0_stage_weights(a, &T.w[lane][0], u, bits, av, nq, gcn);
+                }
+              }
+              if ((av >> lane) & 1u) {  // tables of the epilogue: the k-th active slot's scale and byte offset
+                const int k = __popc(av & ((1u << lane) - 1u));
+                T.dv[k] = sc_v;
+                T.off[k] = (long long)lane * a.out_s_stride * elt;
+              }
+              ++ws;
+            }
+            const int stage = zs & 1;
+            ws_mbar_wait_timed<kWsProducerSleep>(&P.zempty[stage], ((zs >> 1) & 1) ^ 1, timed, t_wait1);
+            {  // Z rows of the super block: one coalesced 512-byte request per in-edge
+              const int uo = u * a.h0;  // element offset of the lane's own source row (N * h0 < 2^31: checked on the host)
+              const float* zc = a.z + cs * 128 + lane * 4;
+              float* zd = &P.z[stage][0][lane * 4];
+#pragma unroll 4
+              for (int j = 0; j < n; ++j) cp_async16_cg(zd + j * 128, zc + __shfl_sync(0xffffffffu, uo, j));
+            }
+            ws_cp_async_arrive(&P.zfull[stage]);
+            const bool last_batch = base + kW2EB >= e1;
+            if (lane == 0) {
+              W2Hdr h;
+              h.v = v; h.av = av; h.n = n; h.cs = cs; h.sb = sb; h.wbuf = wbuf;
+              h.flags = (base == e0 ? WS_FIRST : 0) | (last_batch ? WS_LAST : 0) | ((short_row ? last_pass : true) ? WS_FREE_W : 0);
+              h.pad = 0;
+              P.hdr[stage] = h;
+            }
+            __syncwarp();
+            if (lane == 0) ws_mbar_arrive(&P.zfull[stage]);  // releases the header, the tables and the weight rows of all lanes
+            ++zs;
+            base += kW2EB;
+          } while (base < e1);
+        }
+      }
+      if (gcn && s_valid && !early) stage_raw(ws);  // row with many batches: its successor's buffer only now
+    }
+    const int stage = zs & 1;  // end marker
+    ws_mbar_wait<kWsProducerSleep>(&P.zempty[stage], ((zs >> 1) & 1) ^ 1);
+    if (lane == 0) P.hdr[stage].flags = WS_END;
+    ws_cp_async_arrive(&P.zfull[stage]);
+    __syncwarp();
+    if (lane == 0) ws_mbar_arrive(&P.zfull[stage]);
+    if (timed && lane == 0) {
+      a.dbg[0] = (unsigned long long)(clock64() - t_start); a.dbg[1] = t_wait0; a.dbg[2] = t_wait1; a.dbg[3] = zs;
+    }
+  } else {
+    const float lower = a.act_fn == XPGNN_ACT_RELU ? 0.0f : -INFINITY;
+    const float gcn1 = gcn ? 1.0f : 0.0f, pre1 = a.prescale ? 1.0f : 0.0f;
+    const int g = lane >> 4, c = lane & 15;
+    float2 acc[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) acc[k] = make_float2(0.f, 0.f);
+    for (uint32_t zs = 0;; ++zs) {
+      const int stage = zs & 1;
+      ws_mbar_wait_timed<kWsConsumerSleep>(&P.zfull[stage], (zs >> 1) & 1, timed, t_wait0);
+      const W2Hdr h = P.hdr[stage];
+      if (h.flags & WS_END) {
+        if (timed && lane == 0) {
+          a.dbg[4] = (unsigned long long)(clock64() - t_start); a.dbg[5] = t_wait0; a.dbg[6] = t_fma; a.dbg[7] = zs;
+        }
+        break;
+      }
+      // epilogue operands: loads only, in flight during the FMAs.  ex = the row's own Z (GCN self loop) | the SAGE root term
+      float4 ex[2], add[2];
+#pragma unroll
+      for (int b = 0; b < 2; ++b) ex[b] = add[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (h.flags & WS_LAST) {
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          if (gcn) ex[b] = __ldg(reinterpret_cast<const float4*>(a.z + (int64_t)h.v * a.h0 + h.cs * 128 + b * 64 + 4 * c));
+          else if (a.r0c && (PLAIN || a.finish))
+            ex[b] = __ldg(reinterpret_cast<const float4*>(a.r0c + (int64_t)(h.cs * 4 + b * 2 + (c >> 3)) * a.r0_chunk_stride + (int64_t)h.v * 32 + ((4 * c) & 31)));
+          if (a.bias && (PLAIN || a.finish)) add[b] = __ldg(reinterpret_cast<const float4*>(a.bias + h.cs * 128 + b * 64 + 4 * c));
+        }
+      }
+      if (h.flags & WS_FIRST) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) acc[k] = make_float2(0.f, 0.f);
+      }
+      const int n_slots = __popc(h.av);
+      const W2W& T = P.wb[h.wbuf];
+      const long long t_f0 = timed ? clock64() : 0;
+      ws2_fma_switch((min(16, n_slots - 16 * h.sb) + 3) >> 2, &T.w[0][16 * h.sb + 2 * g], &P.z[stage][0][4 * c], h.n, acc);
+      if (timed) t_fma += (unsigned long long)(clock64() - t_f0);
+      __syncwarp();
+      if (lane == 0) ws_mbar_arrive(&P.zempty[stage]);  // before the epilogue: the next stage's rows fly during it
+      if (h.flags & WS_LAST) {
+        if (!gcn) {  // SAGE: no self term (its weight is 0), the root term joins the addend
+#pragma unroll
+          for (int b = 0; b < 2; ++b) { add[b].x += ex[b].x; add[b].y += ex[b].y; add[b].z += ex[b].z; add[b].w += ex[b].w; }
+        }
+        ws2_epilogue<SIGMOID, OUT16, PLAIN>(a, T, h.v, n_slots, h.cs, h.sb, lane, gcn1, pre1, lower, acc, ex, add);
       }
       if (h.flags & WS_FREE_W) {
         __syncwarp();
@@ -1549,31 +1876,42 @@ static bool compact_act16(const xpgnn_plan_t* p) {
 // layer-0 row kernel over the rows that are not hub rows: warp specialised by default, XPGNN_L0_WS=0 selects the
 // one-warp-per-row kernel (same arithmetic, same order: bit-identical)
 static int launch_l0_rows(const L0RowsArgs& r, bool sigmoid, bool out16, int n_rows, cudaStream_t st) {
-  static const bool ws_env = !(getenv("XPGNN_L0_WS") && std::string(getenv("XPGNN_L0_WS")) == "0");
-  const bool ws = ws_env && (int64_t)r.N * r.h0 < (int64_t(1) << 31);  // 32-bit source-row offsets in the producer
-  const int64_t row_groups = std::max<int64_t>(ceil_div(n_rows, 8 * kRowGrab), 1);
+  // XPGNN_L0_WS: 1 (default) warp specialised, column-block tiling; 2 warp specialised, slot x column tiling (widths % 128 == 0:
+  // 40 % fewer shared-memory wavefronts and fewer cycles, but a lower clock under the power cap -- 6.2 against 5.3 ms at C3);
+  // 0 one warp per row.  Read per call so that the tests can compare the three.
+  const int ws_env = getenv("XPGNN_L0_WS") ? atoi(getenv("XPGNN_L0_WS")) : 1;
+  int ws = (int64_t)r.N * r.h0 < (int64_t(1) << 31) ? ws_env : 0;  // 32-bit source-row offsets in the producers
+  if (ws == 2 && r.h0 % 128 != 0) ws = 1;
+  const bool plain = !r.accumulate && r.finish;
   if (ws) {
-    const bool plain = !r.accumulate && r.finish;
-    void (*k)(const L0RowsArgs) = out16  ? (sigmoid ? l0_ws_kernel<true, true, true> : l0_ws_kernel<false, true, true>)
-                                  : plain ? (sigmoid ? l0_ws_kernel<true, false, true> : l0_ws_kernel<false, false, true>)
-                                          : (sigmoid ? l0_ws_kernel<true, false, false> : l0_ws_kernel<false, false, false>);
-    XP_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmemBytes));
+    void (*k)(const L0RowsArgs);
+    if (ws == 2)
+      k = out16  ? (sigmoid ? l0_ws2_kernel<true, true, true> : l0_ws2_kernel<false, true, true>)
+        : plain ? (sigmoid ? l0_ws2_kernel<true, false, true> : l0_ws2_kernel<false, false, true>)
+                : (sigmoid ? l0_ws2_kernel<true, false, false> : l0_ws2_kernel<false, false, false>);
+    else
+      k = out16  ? (sigmoid ? l0_ws_kernel<true, true, true> : l0_ws_kernel<false, true, true>)
+        : plain ? (sigmoid ? l0_ws_kernel<true, false, true> : l0_ws_kernel<false, false, true>)
+                : (sigmoid ? l0_ws_kernel<true, false, false> : l0_ws_kernel<false, false, false>);
+    const int smem = ws == 2 ? kW2SmemBytes : kWsSmemBytes;
+    XP_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     static const bool dbg_on = getenv("XPGNN_L0_DBG") != nullptr;  // synchronises; diagnostics only
     L0RowsArgs rr = r;
     if (dbg_on) {
       XP_CHECK(cudaMalloc(&rr.dbg, 8 * sizeof(unsigned long long)));
       XP_CHECK(cudaMemsetAsync(rr.dbg, 0, 8 * sizeof(unsigned long long), st));
     }
-    XP_LAUNCH(k, (int)std::min<int64_t>(std::max<int64_t>(ceil_div(n_rows, kWsPairs * kWsGrab), 1), kNumSMs), 2 * kWsPairs * 32, kWsSmemBytes, st, rr);
+    XP_LAUNCH(k, (int)std::min<int64_t>(std::max<int64_t>(ceil_div(n_rows, kWsPairs * kWsGrab), 1), kNumSMs), 2 * kWsPairs * 32, smem, st, rr);
     if (dbg_on) {
       unsigned long long h[8];
       XP_CHECK(cudaStreamSynchronize(st));
       XP_CHECK(cudaMemcpy(h, rr.dbg, sizeof h, cudaMemcpyDeviceToHost));
       XP_CHECK(cudaFree(rr.dbg));
-      fprintf(stderr, "[l0_ws] producer total %llu wait_wempty %llu wait_zempty %llu stages %llu | consumer total %llu wait_zfull %llu fma %llu stages %llu (cycles)\n",
-              h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
+      fprintf(stderr, "[l0_ws%d] producer total %llu wait_wempty %llu wait_zempty %llu stages %llu | consumer total %llu wait_zfull %llu fma %llu stages %llu (cycles)\n",
+              ws, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
     }
   } else {
+    const int64_t row_groups = std::max<int64_t>(ceil_div(n_rows, 8 * kRowGrab), 1);
     void (*k)(const L0RowsArgs) = out16 ? (sigmoid ? l0_rows_kernel<true, false, true> : l0_rows_kernel<false, false, true>)
                                         : (sigmoid ? l0_rows_kernel<true, false, false> : l0_rows_kernel<false, false, false>);
     XP_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kL0SmemBytes));

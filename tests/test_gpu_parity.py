@@ -431,6 +431,34 @@ def test_compact_path_randomized(seed, lib, monkeypatch):
         np.testing.assert_allclose(y16, y, rtol=2e-2, atol=2e-3)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["gcn", "sage"])
+def test_layer0_kernel_variants_agree(kind, lib, monkeypatch):
+    """The three layer-0 row kernels (XPGNN_L0_WS = 0 one warp per row, 1 warp specialised with column blocks, 2 warp
+    specialised with slot x column tiles) do the same FMAs in the same order: outputs agree to rounding of the epilogue,
+    on a graph with isolated rows, rows longer than one stage (> 16 / > 32 in-edges) and more than 16 active slots."""
+    from bikg_graph_explainability_public_b200.engine import GraphSpec, MaskedForward
+    from bikg_graph_explainability_public_b200.lowering import lower
+    from oracle.xpgnn_oracle import kernel_output
+
+    x, ei, arch, mask, q = _random_model_case(11, kind, n=3000, e=60000, f=32, hidden=(128, 128), s=64)
+    ei[1, :6000] = ei[1, :6000] % 50          # 50 rows with ~120 extra in-edges: several stages per pass
+    mask[:, ::7] = True                       # every 7th node active in all 32 slots of a word: two slot blocks
+    s, n = mask.shape
+    _, y_ref = kernel_output(mask.numpy(), x, ei.numpy(), arch, q)
+    y_ref = y_ref.numpy().reshape(-1)
+    act = _pack(lib, mask)
+    g = GraphSpec(x.cuda(), ei.cuda(), [0, n])
+    ys = []
+    for mode in ("0", "1", "2"):
+        monkeypatch.setenv("XPGNN_L0_WS", mode)
+        y = MaskedForward(g, lower(arch), [q, 3])(act, s).cpu().numpy()
+        np.testing.assert_allclose(y[:, 0], y_ref, rtol=Y_RTOL, atol=Y_ATOL)
+        ys.append(y)
+    np.testing.assert_allclose(ys[1], ys[0], rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(ys[2], ys[0], rtol=2e-6, atol=1e-7)
+
+
 @pytest.mark.parametrize("name", ["c4_tiny", "c2_wide", "c2_wide2"])
 def test_hetero_compact_path_matches_oracle(name, lib, monkeypatch):
     """Hetero compact path (per-relation compaction, relations into one destination type accumulate, merged root
