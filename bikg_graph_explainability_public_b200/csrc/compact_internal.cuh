@@ -1,0 +1,83 @@
+// Shared by the compact-path translation units: compact.cu (per-tile compaction, list-driven SpMM, head, the two
+// drivers) and compact_l0.cu (layer-0 row kernels).
+#pragma once
+#include "engine_internal.cuh"
+
+namespace xpgnn {
+
+// Dynamic row scheduling for the row-per-warp kernels: a warp takes kRowGrab consecutive rows at a time from a
+// global counter.  (A static stride is badly unbalanced on power-law graphs: with R-MAT ids the in-degree is a
+// function of the id's bit pattern, and a stride that is a multiple of 64 hands some CTAs rows ~1000x heavier.)
+constexpr int kRowGrab = 4;
+__device__ __forceinline__ int grab_rows(int32_t* counter, int lane) {
+  int base = 0;
+  if (lane == 0) base = atomicAdd(counter, kRowGrab);
+  return __shfl_sync(0xffffffffu, base, 0);
+}
+
+
+// ------------------------------------------------------------------------------------------
+// layer 0, row-outer: the gathered operand Z = X W^T is coalition invariant, so a neighbour row crosses
+// the L2 fabric ONCE per destination row and is reused from registers for every coalition slot of the tile
+// (the list-driven kernel below moves it once per (slot, edge): 82 GB per C3 tile against ~12 GB here).
+// ------------------------------------------------------------------------------------------
+struct L0RowsArgs {
+  const int32_t* rowptr;
+  const int32_t* col;
+  const uint32_t* ebits;
+  const uint32_t* act;
+  int W, w, b0, nb, N;
+  const float* scale;        // [N][32] by bit of the word
+  const float* z;            // [N][h0] row-major
+  int h0;
+  const float* bias;         // GCN bias or NULL
+  const float* r0c;          // SAGE: b + X W_root^T, chunk-major (cw = 32) or NULL
+  int64_t r0_chunk_stride;
+  float* out;                // chunk-major (cw = 32) activations of the tile
+  int64_t out_s_stride, out_chunk_stride;
+  int kind, act_fn, prescale;
+  const int32_t* long_rows;  // rows with more than long_threshold in-edges (hub rows): one CTA each in the LONG variant
+  int long_threshold;        // 0: no splitting
+  int32_t* counter;          // row counter of the dynamic schedule (zero at launch)
+  // several relations into one destination type (HeteroConv sum): the first writes, the others add, the last finishes
+  int row_lo, row_hi;        // destination range of the relation (rows outside are skipped)
+  int accumulate;            // 1: add the partial sum already stored in `out`
+  int finish;                // 1: add the bias / addend, apply the activation (and pre-scale); 0: store the partial sum
+  unsigned long long* dbg;   // XPGNN_L0_DBG: cycle counters of warp pair 0 of CTA 0 (diagnostics only)
+};
+
+constexpr int kLongRow = 1024;    // in-edges above which a destination row is processed by a whole CTA
+constexpr int kLongCompact = 256; // active in-edges above which a compact row is processed by a whole CTA (SpMM)
+
+constexpr int kMaxL0Rel = 12;
+struct L0Rel {
+  const int32_t* rowptr;
+  const int32_t* col;
+  const uint32_t* ebits;
+  const float* scale;  // [.][32] by bit of the word, indexed by global node id (biased pointer)
+  const float* z;      // [.][h0] row-major Z_r = X W_r^T, indexed by global source id (biased pointer)
+  int kind;
+};
+struct L0MultiArgs {
+  L0Rel rel[kMaxL0Rel];
+  int n_rel;
+  const uint32_t* act;
+  int W, w, b0, nb, h0;
+  const float* r0c;          // sum over the relations of b_r (+ X W_root,r^T), chunk-major
+  int64_t r0_chunk_stride;
+  float* out;
+  int64_t out_s_stride, out_chunk_stride;
+  int act_fn;
+  int32_t* counter;
+  int row_lo, row_hi;
+};
+
+// ---- launchers of compact_l0.cu (return non-zero on a CUDA error, like every launch helper of the engine) ----
+// rows that are not hub rows: warp specialised by default (XPGNN_L0_WS selects the variant)
+int launch_l0_rows(const L0RowsArgs& r, bool sigmoid, bool out16, int n_rows, cudaStream_t st);
+// hub rows (r.long_rows, more than r.long_threshold in-edges): one CTA per row
+int launch_l0_long_rows(const L0RowsArgs& r, bool sigmoid, bool out16, int n_long, cudaStream_t st);
+// all relations into one destination type in one pass (HeteroConv sum)
+int launch_l0_multi(const L0MultiArgs& a, bool sigmoid, cudaStream_t st);
+
+}  // namespace xpgnn
