@@ -68,6 +68,8 @@ __global__ void __launch_bounds__(256) masked_scale_kernel(const int32_t* __rest
 // the tile looped inside so that the row's column indices / activity words are read once.
 // ------------------------------------------------------------------------------------------
 constexpr int kLongRowTile = 1024;  // in-edges above which the tile path hands a row to a whole CTA
+constexpr int kHubRows = 16;        // launches with at most this many rows split their hub rows over kHubSlices CTAs each
+constexpr int kHubSlices = 64;
 
 struct SpmmArgs {
   const int32_t* rowptr;
@@ -89,6 +91,7 @@ struct SpmmArgs {
   int ld_out;
   int accumulate, act_fn, H;
   int has_long_rows;         // the CSR has rows above kLongRowTile in-edges (host knows: max degree per unique CSR)
+  float* hub_partial;        // [kHubRows][kHubSlices][32][H] scratch of the sliced hub-row path (tiny launches), or NULL
 };
 
 template <int VEC>
@@ -224,6 +227,103 @@ __global__ void __launch_bounds__(256, 4) spmm_masked_kernel(const SpmmArgs a) {
           o.store(op);
         }
       }
+    }
+  }
+}
+
+// Hub rows of a TINY launch (the pruned last layer of a query is one row; a hub query's row has e.g. 82 K in-edges): one
+// CTA per row leaves 147 SMs idle, so the row's in-edges are cut into kHubSlices slices, one CTA each (its warps split the
+// slots as above), partial sums go to scratch and a second kernel adds the slices in a fixed order (deterministic) and
+// runs the row epilogue.
+template <int VEC>
+__global__ void __launch_bounds__(256, 4) spmm_hub_slices_kernel(const SpmmArgs a) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int r = blockIdx.x / kHubSlices, j = blockIdx.x % kHubSlices;
+  const int v = a.rows ? a.rows[r] : a.row_lo + r;
+  if (v < a.dst_lo || v >= a.dst_hi) return;
+  const int e0 = a.rowptr[v], e1 = a.rowptr[v + 1], deg = e1 - e0;
+  if (deg <= kLongRowTile) return;
+  const int per = ((deg + kHubSlices - 1) / kHubSlices + 31) & ~31;  // slice length, whole 32-edge batches
+  const int bs = e0 + j * per, be = min(e1, bs + per);
+  const int chunks = (a.H + 32 * VEC - 1) / (32 * VEC);
+  for (int cc = 0; cc < chunks; ++cc) {
+    const int c0 = cc * 32 * VEC + lane * VEC;
+    const bool colok = c0 < a.H;
+    for (int s = wib; s < a.n_bits; s += wpb) {
+      const int b = a.b0 + s;
+      const float* in_s = a.in + (int64_t)s * a.in_s_stride;
+      float acc[VEC];
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) acc[i] = 0.0f;
+      for (int base = bs; base < be; base += 32) {
+        const int e = base + lane;
+        int u = -1;
+        uint32_t bits = 0;
+        if (e < be) {
+          u = __ldg(a.col + e);
+          bits = __ldg(a.ebits + e);
+        }
+        gather_edges<VEC>(a, __ballot_sync(0xffffffffu, (bits >> b) & 1u), u, b, in_s, c0, colok, acc);
+      }
+      if (colok) {
+        Vec<VEC> o;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) o.v[i] = acc[i];
+        o.store(a.hub_partial + (((int64_t)r * kHubSlices + j) * 32 + s) * a.H + c0);
+      }
+    }
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) spmm_hub_reduce_kernel(const SpmmArgs a) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int r = blockIdx.x;
+  const int v = a.rows ? a.rows[r] : a.row_lo + r;
+  if (v < a.dst_lo || v >= a.dst_hi) return;
+  if (a.rowptr[v + 1] - a.rowptr[v] <= kLongRowTile) return;
+  const int chunks = (a.H + 32 * VEC - 1) / (32 * VEC);
+  for (int cc = 0; cc < chunks; ++cc) {
+    const int c0 = cc * 32 * VEC + lane * VEC;
+    if (c0 >= a.H) continue;
+    for (int s = wib; s < a.n_bits; s += wpb) {
+      const float* in_s = a.in + (int64_t)s * a.in_s_stride;
+      float acc[VEC];
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) acc[i] = 0.0f;
+      for (int j = 0; j < kHubSlices; ++j) {
+        Vec<VEC> pj;
+        pj.load(a.hub_partial + (((int64_t)r * kHubSlices + j) * 32 + s) * a.H + c0);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] += pj.v[i];
+      }
+      const float dv = a.scale[(int64_t)v * 32 + a.b0 + s];
+      Vec<VEC> o;
+      if (a.kind == XPGNN_CONV_GCN) {
+        Vec<VEC> self;
+        self.load(in_s + (int64_t)v * a.ld_in + c0);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) o.v[i] = dv * fmaf(dv, self.v[i], acc[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) o.v[i] = dv * acc[i];
+      }
+      if (a.addend) {
+        Vec<VEC> ad;
+        ad.load(a.addend + (int64_t)v * a.ld_add + c0);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) o.v[i] += ad.v[i];
+      }
+      float* op = a.out + (int64_t)s * a.out_s_stride + (int64_t)v * a.ld_out + c0;
+      if (a.accumulate) {
+        Vec<VEC> prev;
+        prev.load(op);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) o.v[i] += prev.v[i];
+      }
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) o.v[i] = apply_act(o.v[i], a.act_fn);
+      o.store(op);
     }
   }
 }
@@ -391,7 +491,12 @@ static int launch_spmm(const SpmmArgs& s, cudaStream_t st) {
                     (!s.addend || (s.ld_add % 4 == 0 && (uintptr_t)s.addend % 16 == 0));
   void (*k)(const SpmmArgs) = vec4 ? spmm_masked_kernel<4, false> : spmm_masked_kernel<1, false>;
   XP_LAUNCH(k, grid, 256, 0, st, s);
-  if (s.has_long_rows) {  // hub rows: one CTA per row, warps split the slots
+  if (s.has_long_rows && s.hub_partial && s.n_rows <= kHubRows) {  // few rows: every hub row over kHubSlices CTAs
+    void (*ks)(const SpmmArgs) = vec4 ? spmm_hub_slices_kernel<4> : spmm_hub_slices_kernel<1>;
+    void (*kr)(const SpmmArgs) = vec4 ? spmm_hub_reduce_kernel<4> : spmm_hub_reduce_kernel<1>;
+    XP_LAUNCH(ks, s.n_rows * kHubSlices, 256, 0, st, s);
+    XP_LAUNCH(kr, s.n_rows, 256, 0, st, s);
+  } else if (s.has_long_rows) {  // hub rows: one CTA per row, warps split the slots
     const int grid_long = (int)std::min<int64_t>(s.n_rows, (int64_t)kNumSMs * 8);
     void (*kl)(const SpmmArgs) = vec4 ? spmm_masked_kernel<4, true> : spmm_masked_kernel<1, true>;
     XP_LAUNCH(kl, grid_long, 256, 0, st, s);
@@ -411,6 +516,7 @@ struct Layout {
   std::vector<std::vector<float*>> wroot; // per layer >= 1, per relation: sum of the SAGE root weights of its destination group
   std::vector<int32_t*> rows;  // per layer (prune)
   int32_t* row_counts = nullptr;
+  float* hub_partial = nullptr;  // sliced hub rows of tiny launches (prune)
   int64_t bytes = 0;
 };
 
@@ -476,6 +582,7 @@ static Layout carve(const xpgnn_plan_t* p, void* ws, int64_t cap, int tile, cons
   if (p->prune) {
     for (int l = 0; l < p->n_layers; ++l) lay.rows.push_back(b.take<int32_t>(N));
     lay.row_counts = b.take<int32_t>(p->n_layers);
+    lay.hub_partial = b.take<float>((int64_t)kHubRows * kHubSlices * 32 * std::max(hmax, kmax));
   }
   lay.bytes = (b.off + 255) & ~255ll;
   return lay;
@@ -694,7 +801,7 @@ int xpgnn_forward(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32_t
           s.scale = lay.scale[umap[l][r]]; s.kind = R.conv_kind; s.has_long_rows = max_deg[umap[l][r]] > kLongRowTile;
           s.rows = p->prune ? lay.rows[l] : nullptr;
           s.n_rows = p->prune ? n_rows[l] : (R.dst_hi - R.dst_lo);
-          s.row_lo = R.dst_lo; s.dst_lo = R.dst_lo; s.dst_hi = R.dst_hi;
+          s.row_lo = R.dst_lo; s.dst_lo = R.dst_lo; s.dst_hi = R.dst_hi; s.hub_partial = lay.hub_partial;
           if (l == 0) {  // transform-first: gather the coalition-invariant Z_r, accumulate relations in place
             s.in = lay.zn[r]; s.in_s_stride = 0; s.ld_in = L.h_out; s.H = L.h_out;
             s.addend = first[r] ? lay.r0 : nullptr; s.ld_add = L.h_out;

@@ -7,6 +7,7 @@ the reference).  The reference's ``perturbator`` / ``build_edge_mask`` / ``pertu
 entry points raise ``NotImplementedError`` pointing at ``engine.MaskedForward``.
 """
 import itertools
+import operator
 
 import numpy as np
 import pandas as pd
@@ -14,6 +15,7 @@ import torch
 
 from . import _lib
 from .engine import require_cuda
+from .pathways import all_str
 
 
 def khop_subgraph(edge_index, n_nodes, query, hops):
@@ -96,8 +98,9 @@ class Data:
         sub_et = edge_types.to(subset.device)[edge_mask] if edge_types is not None else None
         if ("node" in problem) or ("graph" in problem):
             idx = subset.cpu().tolist()
-            if all(type(x) is str for x in names):
-                sub_names = [names[i] for i in idx]  # == np.array(names, dtype=str)[subset].tolist(), without the N-string array
+            if all_str(names):
+                sub_names = list(operator.itemgetter(*idx)(names)) if len(idx) > 1 else [names[i] for i in idx]
+                # == np.array(names, dtype=str)[subset].tolist(), without the N-string array
             else:
                 sub_names = np.array(names, dtype=str)[idx].tolist()
         else:

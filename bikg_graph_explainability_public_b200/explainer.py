@@ -18,7 +18,7 @@ from .kernels import shap_weights
 from .lowering import lower
 from .masks import Mask
 from .model import Model
-from .pathways import Pathways
+from .pathways import Pathways, all_str
 from .shard import sharded_eval
 from .wlm import LinearRegression, fit_surrogate
 
@@ -135,7 +135,7 @@ class Explainer:
             ), "No element names have been given and the node name given is not numeric"
             return int(element)
         assert element in names, "Element name '{}' is not present in the graph".format(element)
-        if type(element) is str and all(type(x) is str for x in names):
+        if type(element) is str and all_str(names):
             return names.index(element)  # first match, as np.where(...)[0][0]
         return int(np.where(np.array(names, dtype=str) == element)[0][0])
 

@@ -348,6 +348,13 @@ def test_compact_path_hub_rows(kind, lib, monkeypatch):
     np.testing.assert_allclose(y[:, 0], y_ref.numpy().reshape(-1), rtol=Y_RTOL, atol=Y_ATOL)
     _, y_ref7 = kernel_output(mask.numpy(), x, ei.numpy(), arch, 7)
     np.testing.assert_allclose(y[:, 1], y_ref7.numpy().reshape(-1), rtol=Y_RTOL, atol=Y_ATOL)
+    # pruned mode (what Explainer.run uses): the last layer is ONE hub row -- its in-edges are sliced over many CTAs
+    from bikg_graph_explainability_public_b200.data import khop_subgraph
+    hop = khop_subgraph(ei.cuda(), n, q, 3)[4]
+    yp = MaskedForward(gs, lower(arch), [q], prune=True, hop=hop)(act, s).cpu().numpy()
+    np.testing.assert_allclose(yp[:, 0], y[:, 0], rtol=2e-5, atol=1e-6)
+    yp2 = MaskedForward(gs, lower(arch), [q], prune=True, hop=hop)(act, s).cpu().numpy()
+    np.testing.assert_array_equal(yp2, yp)  # slices are added in a fixed order
     monkeypatch.setenv("XPGNN_LONG", "0")   # hub rows through the row-per-warp kernels
     np.testing.assert_allclose(MaskedForward(gs, lower(arch), [q, 7])(act, s).cpu().numpy(), y, rtol=2e-5, atol=1e-6)
     monkeypatch.setenv("XPGNN_COMPACT", "0")

@@ -45,6 +45,7 @@ def main():
     ap.add_argument("--names", default="str", choices=["str", "int"], help="community members as names or indices")
     ap.add_argument("--queries", type=int, default=2)
     ap.add_argument("--prune", type=int, default=1)
+    ap.add_argument("--profile", action="store_true", help="per-category kernel ms of every query (CUDA events, xpgnn_profile)")
     args = ap.parse_args()
 
     from torch import nn
@@ -90,10 +91,19 @@ def main():
         pw = [list(p) for p in pathways]
         torch.cuda.synchronize()
         t0 = time.perf_counter()
+        if args.profile:
+            from bikg_graph_explainability_public_b200 import _lib
+            _lib.load().xpgnn_profile(1)
         ex = Explainer(x, ei, arch, dict(params), list(names), pw, list(pathway_names))
         cfg, pdf = ex.run(names[q], 1)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        if args.profile:
+            ms, cnt = np.zeros(6), np.zeros(6, dtype=np.int64)
+            _lib.load().xpgnn_profile_read(ms.ctypes.data, cnt.ctypes.data)
+            _lib.load().xpgnn_profile(0)
+            cats = ["masked_degree", "spmm_l0", "spmm_l1", "dense", "head", "compaction"]
+            print(json.dumps({"query": q, "kernel_ms": {c: [round(float(m), 2), int(k)] for c, m, k in zip(cats, ms, cnt)}}), flush=True)
         out.append({"query": q, "in_degree": int(indeg[q]), "seconds": dt, **ex.last_stats,
                     "top_community": None if pdf is None or len(pdf) == 0 else str(pdf.index[0]),
                     "score_checksum": None if pdf is None else float(pdf["score"].abs().sum()), "rank": rank, "world": world})
