@@ -30,20 +30,25 @@ namespace xpgnn {
 // ------------------------------------------------------------------------------------------
 // masked degrees -> per (node, coalition-in-word) normalisation
 // ------------------------------------------------------------------------------------------
+// CTA_ROW: rows above long_threshold in-edges (hub rows of power-law graphs) -- the CTA's warps take interleaved 32-edge
+// batches and add their per-slot counts through shared memory; the warp-per-row launch skips those rows.
+template <bool CTA_ROW>
 __global__ void __launch_bounds__(256) masked_scale_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                                                            const uint32_t* __restrict__ act, int W, int w, int row_lo, int row_hi,
                                                            int kind, float* __restrict__ scale, uint32_t* __restrict__ ebits,
-                                                           unsigned long long* __restrict__ tile_active) {
+                                                           unsigned long long* __restrict__ tile_active, int long_threshold) {
   __shared__ unsigned long long s_active[32];
+  __shared__ int s_cnt[8][32];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   if (threadIdx.x < 32) s_active[threadIdx.x] = 0;
   __syncthreads();
   unsigned long long my_active = 0;
-  for (int v = row_lo + blockIdx.x * wpb + wib; v < row_hi; v += gridDim.x * wpb) {
+  for (int v = row_lo + (CTA_ROW ? blockIdx.x : blockIdx.x * wpb + wib); v < row_hi; v += CTA_ROW ? gridDim.x : gridDim.x * wpb) {
     const int e0 = rowptr[v], e1 = rowptr[v + 1];
+    if (long_threshold > 0 && (CTA_ROW ? e1 - e0 <= long_threshold : e1 - e0 > long_threshold)) continue;  // CTA uniform when CTA_ROW
     const uint32_t av = act[(int64_t)v * W + w];
     int cnt = 0;
-    for (int base = e0; base < e1; base += 32) {
+    for (int base = e0 + (CTA_ROW ? 32 * wib : 0); base < e1; base += CTA_ROW ? 32 * wpb : 32) {
       const int e = base + lane;
       uint32_t bits = 0;
       if (e < e1) {
@@ -52,6 +57,14 @@ __global__ void __launch_bounds__(256) masked_scale_kernel(const int32_t* __rest
       }
       const int n = min(32, e1 - base);
       for (int j = 0; j < n; ++j) cnt += (__shfl_sync(0xffffffffu, bits, j) >> lane) & 1u;
+    }
+    if (CTA_ROW) {
+      s_cnt[wib][lane] = cnt;
+      __syncthreads();
+      cnt = 0;
+      for (int k = 0; k < wpb; ++k) cnt += s_cnt[k][lane];
+      __syncthreads();
+      if (wib != 0) continue;
     }
     scale[(int64_t)v * 32 + lane] = (kind == XPGNN_CONV_GCN) ? 1.0f / sqrtf(1.0f + (float)cnt) : 1.0f / (float)max(cnt, 1);
     my_active += cnt;
@@ -783,8 +796,12 @@ int xpgnn_forward(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32_t
       const int rows = uniq[i].hi - uniq[i].lo;
       const int grid = (int)std::min<int64_t>(std::max<int64_t>(ceil_div(rows, 8), 1), (int64_t)kNumSMs * 8);
       ProfScope ps(PROF_SCALE, st);
-      XP_LAUNCH(masked_scale_kernel, grid, 256, 0, st, uniq[i].rowptr, uniq[i].col, act, W, w, uniq[i].lo, uniq[i].hi,
-                uniq[i].kind, lay.scale[i], lay.ebits[i], lay.tile_active);
+      const int thr = max_deg[i] > kLongRowTile ? kLongRowTile : 0;
+      XP_LAUNCH(masked_scale_kernel<false>, grid, 256, 0, st, uniq[i].rowptr, uniq[i].col, act, W, w, uniq[i].lo, uniq[i].hi,
+                uniq[i].kind, lay.scale[i], lay.ebits[i], lay.tile_active, thr);
+      if (thr > 0)
+        XP_LAUNCH(masked_scale_kernel<true>, (int)std::min<int64_t>(rows, (int64_t)kNumSMs * 8), 256, 0, st, uniq[i].rowptr, uniq[i].col, act, W,
+                  w, uniq[i].lo, uniq[i].hi, uniq[i].kind, lay.scale[i], lay.ebits[i], lay.tile_active, thr);
     }
     for (int b0 = 0; b0 < bits_in_word; b0 += tile) {
       const int nb = std::min(tile, bits_in_word - b0);
