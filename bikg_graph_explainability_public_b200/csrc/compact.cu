@@ -999,7 +999,7 @@ int forward_compact(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32
           r.scale = lay.scale; r.z = lay.zc; r.h0 = L.h_out;
           if (kind == XPGNN_CONV_SAGE_MEAN) { r.r0c = lay.r0c; r.r0_chunk_stride = cstride; }
           else r.bias = R.b_nbr;
-          r.out = cur; r.out_s_stride = hstride; r.out_chunk_stride = cstride;
+          r.out = cur; r.out_s_stride = hstride; r.out_chunk_stride = cstride; r.out_row_stride = 32; r.r0_row_stride = 32;
           r.kind = kind; r.act_fn = L.act; r.prescale = next_gcn;
           ProfScope ps(PROF_SPMM_INVARIANT, st);
           r.long_rows = lay.long_rows; r.long_threshold = n_long > 0 ? kLongRow : 0; r.counter = lay.counters + 13;
@@ -1565,7 +1565,7 @@ int forward_compact_hetero(const xpgnn_plan_t* p, const uint32_t* act, int32_t W
             L0RowsArgs a{};
             a.rowptr = c.rowptr; a.col = c.col; a.ebits = c.ebits; a.act = act; a.W = W; a.w = w; a.b0 = b0; a.nb = nb; a.N = N;
             a.scale = c.scale; a.z = lay.zr[r]; a.h0 = L.h_out; a.r0c = lay.r0c; a.r0_chunk_stride = cstride;
-            a.out = cur; a.out_s_stride = hstride; a.out_chunk_stride = cstride;
+            a.out = cur; a.out_s_stride = hstride; a.out_chunk_stride = cstride; a.out_row_stride = 32; a.r0_row_stride = 32;
             a.kind = R.conv_kind; a.act_fn = L.act; a.prescale = 0;
             a.long_rows = c.long_rows; a.long_threshold = c.n_long > 0 ? kLongRow : 0; a.counter = c.counters + 13;
             a.row_lo = R.dst_lo; a.row_hi = R.dst_hi; a.accumulate = !first[l][r]; a.finish = last[l][r];

@@ -43,6 +43,11 @@ struct L0RowsArgs {
   int row_lo, row_hi;        // destination range of the relation (rows outside are skipped)
   int accumulate;            // 1: add the partial sum already stored in `out`
   int finish;                // 1: add the bias / addend, apply the activation (and pre-scale); 0: store the partial sum
+  // fp32 outputs / addends: element (chunk, row v, column c of the chunk) sits at chunk * chunk_stride + v * row_stride + c --
+  // chunk-major activations of the compact path: row_stride 32; a row-major [N][ld] buffer (tile path): chunk_stride 32, row_stride ld
+  int out_row_stride, r0_row_stride;
+  const int32_t* rows;       // optional row list (pruned mode of the tile path): row i of the launch is rows[i], i < n_list
+  int n_list;
   unsigned long long* dbg;   // XPGNN_L0_DBG: cycle counters of warp pair 0 of CTA 0 (diagnostics only)
 };
 

@@ -77,7 +77,7 @@ __device__ __forceinline__ void l0_epilogue_operands(const L0RowsArgs& a, int v,
   if (gcn) self = __ldg(reinterpret_cast<const float2*>(a.z + (int64_t)v * a.h0 + cb * 64 + lane * 2));
   if (a.bias && a.finish) add = __ldg(reinterpret_cast<const float2*>(a.bias + cb * 64 + lane * 2));
   if (a.r0c && a.finish) {
-    const float2 r = __ldg(reinterpret_cast<const float2*>(a.r0c + (int64_t)(cb * 2 + (lane >> 4)) * a.r0_chunk_stride + (int64_t)v * 32 + (lane & 15) * 2));
+    const float2 r = __ldg(reinterpret_cast<const float2*>(a.r0c + (int64_t)(cb * 2 + (lane >> 4)) * a.r0_chunk_stride + (int64_t)v * a.r0_row_stride + (lane & 15) * 2));
     add.x += r.x; add.y += r.y;
   }
 }
@@ -87,7 +87,7 @@ __device__ __forceinline__ void l0_epilogue_operands(const L0RowsArgs& a, int v,
 template <bool SIGMOID, bool OUT16>
 __device__ __forceinline__ void l0_epilogue(const L0RowsArgs& a, int v, uint32_t av, int n_slots, int cb, int lane, float sc_v, bool gcn,
                                             float lower, const float2 (&acc)[32], const float2 self, const float2 add) {
-  const int64_t cm_off = (int64_t)(cb * 2 + (lane >> 4)) * a.out_chunk_stride + (int64_t)v * 32 + (lane & 15) * 2;
+  const int64_t cm_off = (int64_t)(cb * 2 + (lane >> 4)) * a.out_chunk_stride + (int64_t)v * a.out_row_stride + (lane & 15) * 2;
   float* outp = a.out + cm_off - (int64_t)a.b0 * a.out_s_stride;
   // bf16 layout: one 64-column block is one chunk, a lane's 2 columns are one bf162
   __nv_bfloat16* outp16 = reinterpret_cast<__nv_bfloat16*>(a.out) + (int64_t)cb * a.out_chunk_stride + (int64_t)v * 64 + lane * 2 -
@@ -171,9 +171,10 @@ __global__ void __launch_bounds__(256, 2) l0_rows_kernel(const L0RowsArgs a) {
   const bool gcn = a.kind == XPGNN_CONV_GCN;
   const int ncb = a.h0 / 64;
   const float lower = a.act_fn == XPGNN_ACT_RELU ? 0.0f : -INFINITY;
-  const int n_rows = a.row_hi - a.row_lo;  // destination range of the relation
+  const int n_rows = a.rows ? a.n_list : a.row_hi - a.row_lo;  // row list (pruned mode) | destination range of the relation
   for (int vb = LONG ? 0 : grab_rows(a.counter, lane); vb < n_rows; vb = LONG ? n_rows : grab_rows(a.counter, lane))
-  for (int v = LONG ? a.long_rows[blockIdx.x] : a.row_lo + vb; v < (LONG ? a.N : a.row_lo + min(n_rows, vb + kRowGrab)); v += LONG ? a.N : 1) {
+  for (int vi = LONG ? 0 : vb; vi < (LONG ? 1 : min(n_rows, vb + kRowGrab)); ++vi) {
+    const int v = LONG ? a.long_rows[blockIdx.x] : (a.rows ? a.rows[vi] : a.row_lo + vi);
     const uint32_t av = a.act[(int64_t)v * a.W + a.w] & live;
     if (!av) continue;  // LONG: the same row for the whole CTA, so every warp leaves together
     const int n_slots = __popc(av), nq = (n_slots + 3) >> 2;
@@ -346,7 +347,7 @@ __device__ __forceinline__ void l0_epilogue_tab(const L0RowsArgs& a, const WsW& 
                                                 float lower, const float2 (&acc)[32], const float2 self, const float2 add) {
   char* outp = OUT16 ? reinterpret_cast<char*>(reinterpret_cast<__nv_bfloat16*>(a.out) + (int64_t)cb * a.out_chunk_stride + (int64_t)v * 64 + lane * 2 -
                                                (int64_t)a.b0 * a.out_s_stride)
-                     : reinterpret_cast<char*>(a.out + (int64_t)(cb * 2 + (lane >> 4)) * a.out_chunk_stride + (int64_t)v * 32 + (lane & 15) * 2 -
+                     : reinterpret_cast<char*>(a.out + (int64_t)(cb * 2 + (lane >> 4)) * a.out_chunk_stride + (int64_t)v * a.out_row_stride + (lane & 15) * 2 -
                                                (int64_t)a.b0 * a.out_s_stride);
   const int nq = (n_slots + 3) >> 2;
   const float pre0 = 1.0f - pre1;
@@ -410,21 +411,23 @@ __global__ void __launch_bounds__(2 * kWsPairs * 32, 1) l0_ws_kernel(const L0Row
   unsigned long long t_wait0 = 0, t_wait1 = 0, t_fma = 0;
   const long long t_start = timed ? clock64() : 0;
   if (producer) {
-    const int n_rows = a.row_hi - a.row_lo;
+    const int n_rows = a.rows ? a.n_list : a.row_hi - a.row_lo;  // row list (pruned mode) | destination range
     uint32_t zs = 0, ws = 0;  // stages / weight buffers handed over so far
     // Row iterator with the metadata one row ahead: (active word, row pointers) of the NEXT row are loaded when the
     // current row starts, its first 32 (source, edge-activity) pairs once the current row's first stage is out, so the
     // per-row chain of dependent loads shrinks to scales -> Z.
-    int g_lo = 0, g_hi = 0;
+    int g_lo = 0, g_hi = 0, g_base = 0, g_row = 0;
     auto next_v = [&]() -> int {
       if (g_lo >= g_hi) {
         int base = 0;
         if (lane == 0) base = atomicAdd(a.counter, kWsGrab);
-        g_lo = __shfl_sync(0xffffffffu, base, 0);
+        g_lo = g_base = __shfl_sync(0xffffffffu, base, 0);
         g_hi = min(n_rows, g_lo + kWsGrab);
         if (g_lo >= n_rows) return -1;
+        if (a.rows) g_row = lane < g_hi - g_lo ? __ldg(a.rows + g_lo + lane) : 0;  // the grab's list entries in one load
       }
-      return a.row_lo + g_lo++;
+      const int i = g_lo++;
+      return a.rows ? __shfl_sync(0xffffffffu, g_row, i - g_base) : a.row_lo + i;
     };
     const int elt = OUT16 ? 2 : 4;  // bytes per stored activation element
     int v_n = next_v();
@@ -575,7 +578,7 @@ __global__ void __launch_bounds__(2 * kWsPairs * 32, 1) l0_ws_kernel(const L0Row
         if (gcn) self = __ldg(reinterpret_cast<const float2*>(a.z + (int64_t)h.v * a.h0 + h.cb * 64 + lane * 2));
         if (a.bias && (PLAIN || a.finish)) add = __ldg(reinterpret_cast<const float2*>(a.bias + h.cb * 64 + lane * 2));
         if (a.r0c && (PLAIN || a.finish))
-          root = __ldg(reinterpret_cast<const float2*>(a.r0c + (int64_t)(h.cb * 2 + (lane >> 4)) * a.r0_chunk_stride + (int64_t)h.v * 32 + (lane & 15) * 2));
+          root = __ldg(reinterpret_cast<const float2*>(a.r0c + (int64_t)(h.cb * 2 + (lane >> 4)) * a.r0_chunk_stride + (int64_t)h.v * a.r0_row_stride + (lane & 15) * 2));
       }
       if (h.flags & WS_FIRST) {
 #pragma unroll
@@ -663,7 +666,7 @@ __device__ __forceinline__ void ws2_epilogue(const L0RowsArgs& a, const W2W& T, 
   for (int b = 0; b < 2; ++b)
     outp[b] = OUT16 ? reinterpret_cast<char*>(reinterpret_cast<__nv_bfloat16*>(a.out) + (int64_t)(cs * 2 + b) * a.out_chunk_stride + (int64_t)v * 64 + 4 * c -
                                               (int64_t)a.b0 * a.out_s_stride)
-                    : reinterpret_cast<char*>(a.out + (int64_t)(cs * 4 + b * 2 + (c >> 3)) * a.out_chunk_stride + (int64_t)v * 32 + ((4 * c) & 31) -
+                    : reinterpret_cast<char*>(a.out + (int64_t)(cs * 4 + b * 2 + (c >> 3)) * a.out_chunk_stride + (int64_t)v * a.out_row_stride + ((4 * c) & 31) -
                                               (int64_t)a.b0 * a.out_s_stride);
   const int np = (min(16, n_slots - 16 * sb) + 3) >> 2;
   const float pre0 = 1.0f - pre1;
@@ -896,7 +899,7 @@ __global__ void __launch_bounds__(2 * kWsPairs * 32, 1) l0_ws2_kernel(const L0Ro
         for (int b = 0; b < 2; ++b) {
           if (gcn) ex[b] = __ldg(reinterpret_cast<const float4*>(a.z + (int64_t)h.v * a.h0 + h.cs * 128 + b * 64 + 4 * c));
           else if (a.r0c && (PLAIN || a.finish))
-            ex[b] = __ldg(reinterpret_cast<const float4*>(a.r0c + (int64_t)(h.cs * 4 + b * 2 + (c >> 3)) * a.r0_chunk_stride + (int64_t)h.v * 32 + ((4 * c) & 31)));
+            ex[b] = __ldg(reinterpret_cast<const float4*>(a.r0c + (int64_t)(h.cs * 4 + b * 2 + (c >> 3)) * a.r0_chunk_stride + (int64_t)h.v * a.r0_row_stride + ((4 * c) & 31)));
           if (a.bias && (PLAIN || a.finish)) add[b] = __ldg(reinterpret_cast<const float4*>(a.bias + h.cs * 128 + b * 64 + 4 * c));
         }
       }
@@ -1025,7 +1028,7 @@ int launch_l0_rows(const L0RowsArgs& r, bool sigmoid, bool out16, int n_rows, cu
   // 0 one warp per row.  Read per call so that the tests can compare the three.
   const int ws_env = getenv("XPGNN_L0_WS") ? atoi(getenv("XPGNN_L0_WS")) : 1;
   int ws = (int64_t)r.N * r.h0 < (int64_t(1) << 31) ? ws_env : 0;  // 32-bit source-row offsets in the producers
-  if (ws == 2 && r.h0 % 128 != 0) ws = 1;
+  if (ws == 2 && (r.h0 % 128 != 0 || r.rows)) ws = 1;  // the slot x column kernel takes whole ranges only
   const bool plain = !r.accumulate && r.finish;
   if (ws) {
     void (*k)(const L0RowsArgs);

@@ -23,7 +23,7 @@
 #include "common.cuh"
 #include "dense_args.cuh"
 #include "fused.cuh"
-#include "engine_internal.cuh"
+#include "compact_internal.cuh"
 
 namespace xpgnn {
 
@@ -471,6 +471,15 @@ __global__ void rows_by_hop_kernel(const int8_t* __restrict__ hop, int N, int ma
   if (v < N && hop[v] >= 0 && hop[v] <= max_hop) rows[atomicAdd(count, 1)] = v;
 }
 
+// hub rows (more than `threshold` in-edges) among the rows of a list
+__global__ void long_rows_of_list_kernel(const int32_t* __restrict__ rows, int n, const int32_t* __restrict__ rowptr, int threshold,
+                                         int32_t* __restrict__ out, int32_t* __restrict__ count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int v = rows[i];
+  if (rowptr[v + 1] - rowptr[v] > threshold) out[atomicAdd(count, 1)] = v;
+}
+
 __global__ void stats_accum_kernel(const unsigned long long* tile_active, int n_bits, int b0, long long mult, int64_t* stats) {
   unsigned long long t = 0;
   for (int b = 0; b < n_bits; ++b) t += tile_active[b0 + b];
@@ -530,6 +539,8 @@ struct Layout {
   std::vector<int32_t*> rows;  // per layer (prune)
   int32_t* row_counts = nullptr;
   float* hub_partial = nullptr;  // sliced hub rows of tiny launches (prune)
+  int32_t* l0_counter = nullptr; // row counter of the layer-0 row kernel (prune)
+  int32_t* l0_long = nullptr;    // hub rows among the layer-0 row list (prune)
   int64_t bytes = 0;
 };
 
@@ -596,6 +607,8 @@ static Layout carve(const xpgnn_plan_t* p, void* ws, int64_t cap, int tile, cons
     for (int l = 0; l < p->n_layers; ++l) lay.rows.push_back(b.take<int32_t>(N));
     lay.row_counts = b.take<int32_t>(p->n_layers);
     lay.hub_partial = b.take<float>((int64_t)kHubRows * kHubSlices * 32 * std::max(hmax, kmax));
+    lay.l0_counter = b.take<int32_t>(64);
+    lay.l0_long = b.take<int32_t>(N);
   }
   lay.bytes = (b.off + 255) & ~255ll;
   return lay;
@@ -711,6 +724,19 @@ int xpgnn_forward(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32_t
 
   // ---- coalition-invariant part of layer 0: Z_r = X W_r^T, R0 = sum_r (b_r + X W_root,r^T) ----
   const xpgnn_layer_t& L0 = p->layers_host[0];
+  // pruned homogeneous stacks run layer 0 through the row-outer kernels of compact_l0.cu (see the layer loop)
+  const bool prune_l0_env = !(getenv("XPGNN_PRUNE_L0") && std::string(getenv("XPGNN_PRUNE_L0")) == "0");
+  const bool prune_l0 = prune_l0_env && p->prune && NL > 1 && L0.n_rel == 1 && L0.rel_host[0].src_lo == 0 && L0.rel_host[0].src_hi == N &&
+                        L0.rel_host[0].dst_lo == 0 && L0.rel_host[0].dst_hi == N && L0.h_out % 64 == 0 &&
+                        (int64_t)N * L0.h_out < (int64_t(1) << 31) && n_rows[0] > n_rows[1];
+  int32_t n_long0 = 0;
+  if (prune_l0 && max_deg[umap[0][0]] > kLongRowTile) {
+    XP_CHECK(cudaMemsetAsync(lay.l0_counter + 1, 0, sizeof(int32_t), st));
+    XP_LAUNCH(long_rows_of_list_kernel, (int)ceil_div(n_rows[0], 256), 256, 0, st, lay.rows[0], n_rows[0], L0.rel_host[0].rowptr, kLongRowTile,
+              lay.l0_long, lay.l0_counter + 1);
+    XP_CHECK(cudaMemcpyAsync(&n_long0, lay.l0_counter + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    XP_CHECK(cudaStreamSynchronize(st));
+  }
   XP_REQUIRE(L0.h_in == p->f_in, "layer 0 input width != feature width");
   XP_CHECK(cudaMemsetAsync(lay.r0, 0, sizeof(float) * (int64_t)N * L0.h_out, st));
   for (int r = 0; r < L0.n_rel; ++r) {
@@ -824,6 +850,32 @@ int xpgnn_forward(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32_t
             s.addend = first[r] ? lay.r0 : nullptr; s.ld_add = L.h_out;
             s.out = cur; s.out_s_stride = hstride; s.ld_out = hmax;
             s.accumulate = !first[r]; s.act_fn = last[r] ? L.act : XPGNN_ACT_NONE;
+            // Pruned homogeneous stacks (what Explainer.run builds for GCN / SAGE models): the needed rows of layer 0 through
+            // the row-outer kernel of the compact path (a source row crosses the fabric once per destination row, not once per
+            // (row, slot)), writing the row-major tile buffer.  It produces the (row, slot) pairs in which the row is ACTIVE --
+            // all that active edges of the next layer gather; the rows the next layer reads in EVERY slot (self / root term
+            // of its own row list) and the hub rows follow through the tile kernel.
+            if (prune_l0) {
+              L0RowsArgs a{};
+              a.rowptr = R.rowptr; a.col = R.col; a.ebits = s.ebits; a.act = act; a.W = W; a.w = w; a.b0 = b0; a.nb = nb; a.N = N;
+              a.scale = s.scale; a.z = lay.zn[r]; a.h0 = L.h_out; a.bias = nullptr;
+              a.r0c = lay.r0; a.r0_chunk_stride = 32; a.r0_row_stride = L.h_out;
+              a.out = cur; a.out_s_stride = hstride; a.out_chunk_stride = 32; a.out_row_stride = hmax;
+              a.kind = R.conv_kind; a.act_fn = L.act; a.prescale = 0;
+              a.long_threshold = n_long0 > 0 ? kLongRowTile : 0; a.counter = lay.l0_counter;
+              a.row_lo = 0; a.row_hi = N; a.rows = lay.rows[0]; a.n_list = n_rows[0]; a.accumulate = 0; a.finish = 1;
+              XP_CHECK(cudaMemsetAsync(lay.l0_counter, 0, sizeof(int32_t), st));
+              {
+                ProfScope ps(PROF_SPMM_INVARIANT, st);
+                if (launch_l0_rows(a, L.act == XPGNN_ACT_SIGMOID, false, n_rows[0], st)) return 1;
+              }
+              if (n_long0 > 0) {  // hub rows of the list: one CTA per row
+                a.long_rows = lay.l0_long;
+                ProfScope ps(PROF_SPMM_INVARIANT, st);
+                if (launch_l0_long_rows(a, L.act == XPGNN_ACT_SIGMOID, false, n_long0, st)) return 1;
+              }
+              s.rows = lay.rows[1]; s.n_rows = n_rows[1];  // every slot of the rows the next layer reads as its own
+            }
             if (launch_spmm(s, st)) return 1;
           } else if (use_fused[l][r]) {  // aggregate + transform in one kernel, the aggregate never leaves the SM
             FusedArgs f{};
