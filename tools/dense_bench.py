@@ -20,5 +20,8 @@ for prec in modes:
         e1.record()
         torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    print("precision %d: %.3f ms  %.1f TFLOP/s (x%d MMAs)  %.0f GB/s" % (
-        prec, ms, 2.0 * m * k * n / ms / 1e9, 3 if prec == 2 else 1, 2.0 * m * k * 4 / ms / 1e6))
+    # accuracy on the first 4096 rows against fp64 (act = ReLU in this call)
+    ref = torch.relu(a[:4096].double() @ w.double().t() + b.double())
+    err = ((out[:4096].double() - ref).abs().max() / ref.abs().max()).item()
+    print("precision %d: %.3f ms  %.1f TFLOP/s (x%d MMAs)  %.0f GB/s  max err / max |ref| %.2e" % (
+        prec, ms, 2.0 * m * k * n / ms / 1e9, 3 if prec == 2 else 1, 2.0 * m * k * 4 / ms / 1e6, err))
