@@ -390,7 +390,7 @@ __device__ __forceinline__ void l0_epilogue_tab(const L0RowsArgs& a, const WsW& 
   }
 }
 
-template <bool SIGMOID, bool OUT16, bool PLAIN>
+template <bool SIGMOID, bool OUT16, bool PLAIN, bool DBG>
 __global__ void __launch_bounds__(2 * kWsPairs * 32, 1) l0_ws_kernel(const L0RowsArgs a) {
   extern __shared__ __align__(128) uint8_t ws_smem[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(2 * kWsPairs * 32, 1) l0_ws_kernel(const L0Row
   const uint32_t live = (a.nb == 32 ? 0xffffffffu : ((1u << a.nb) - 1u)) << a.b0;  // bits of the word in this tile
   const bool gcn = a.kind == XPGNN_CONV_GCN;
   const int ncb = a.h0 / 64;
-  const bool timed = a.dbg != nullptr && blockIdx.x == 0 && (wid == 0 || wid == kWsPairs);
+  const bool timed = DBG && a.dbg != nullptr && blockIdx.x == 0 && (wid == 0 || wid == kWsPairs);  // DBG = false: compiled out
   unsigned long long t_wait0 = 0, t_wait1 = 0, t_fma = 0;
   const long long t_start = timed ? clock64() : 0;
   if (producer) {
@@ -719,7 +719,7 @@ __device__ __forceinline__ void ws2_epilogue(const L0RowsArgs& a, const W2W& T, 
   }
 }
 
-template <bool SIGMOID, bool OUT16, bool PLAIN>
+template <bool SIGMOID, bool OUT16, bool PLAIN, bool DBG>
 __global__ void __launch_bounds__(2 * kWsPairs * 32, 1) l0_ws2_kernel(const L0RowsArgs a) {
   extern __shared__ __align__(128) uint8_t ws_smem[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -736,7 +736,7 @@ __global__ void __launch_bounds__(2 * kWsPairs * 32, 1) l0_ws2_kernel(const L0Ro
   const uint32_t live = (a.nb == 32 ? 0xffffffffu : ((1u << a.nb) - 1u)) << a.b0;  // bits of the word in this tile
   const bool gcn = a.kind == XPGNN_CONV_GCN;
   const int ncs = a.h0 / 128;
-  const bool timed = a.dbg != nullptr && blockIdx.x == 0 && (wid == 0 || wid == kWsPairs);
+  const bool timed = DBG && a.dbg != nullptr && blockIdx.x == 0 && (wid == 0 || wid == kWsPairs);  // DBG = false: compiled out
   unsigned long long t_wait0 = 0, t_wait1 = 0, t_fma = 0;
   const long long t_start = timed ? clock64() : 0;
   if (producer) {
@@ -1031,25 +1031,28 @@ int launch_l0_rows(const L0RowsArgs& r, bool sigmoid, bool out16, int n_rows, cu
   if (ws == 2 && (r.h0 % 128 != 0 || r.rows)) ws = 1;  // the slot x column kernel takes whole ranges only
   const bool plain = !r.accumulate && r.finish;
   if (ws) {
+    static const bool dbg_on = getenv("XPGNN_L0_DBG") != nullptr;  // cycle counters; synchronises; diagnostics only (fp32, ReLU / none)
+    const bool dbg = dbg_on && !out16 && plain && !sigmoid;
     void (*k)(const L0RowsArgs);
     if (ws == 2)
-      k = out16  ? (sigmoid ? l0_ws2_kernel<true, true, true> : l0_ws2_kernel<false, true, true>)
-        : plain ? (sigmoid ? l0_ws2_kernel<true, false, true> : l0_ws2_kernel<false, false, true>)
-                : (sigmoid ? l0_ws2_kernel<true, false, false> : l0_ws2_kernel<false, false, false>);
+      k = dbg    ? l0_ws2_kernel<false, false, true, true>
+        : out16  ? (sigmoid ? l0_ws2_kernel<true, true, true, false> : l0_ws2_kernel<false, true, true, false>)
+        : plain ? (sigmoid ? l0_ws2_kernel<true, false, true, false> : l0_ws2_kernel<false, false, true, false>)
+                : (sigmoid ? l0_ws2_kernel<true, false, false, false> : l0_ws2_kernel<false, false, false, false>);
     else
-      k = out16  ? (sigmoid ? l0_ws_kernel<true, true, true> : l0_ws_kernel<false, true, true>)
-        : plain ? (sigmoid ? l0_ws_kernel<true, false, true> : l0_ws_kernel<false, false, true>)
-                : (sigmoid ? l0_ws_kernel<true, false, false> : l0_ws_kernel<false, false, false>);
+      k = dbg    ? l0_ws_kernel<false, false, true, true>
+        : out16  ? (sigmoid ? l0_ws_kernel<true, true, true, false> : l0_ws_kernel<false, true, true, false>)
+        : plain ? (sigmoid ? l0_ws_kernel<true, false, true, false> : l0_ws_kernel<false, false, true, false>)
+                : (sigmoid ? l0_ws_kernel<true, false, false, false> : l0_ws_kernel<false, false, false, false>);
     const int smem = ws == 2 ? kW2SmemBytes : kWsSmemBytes;
     XP_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    static const bool dbg_on = getenv("XPGNN_L0_DBG") != nullptr;  // synchronises; diagnostics only
     L0RowsArgs rr = r;
-    if (dbg_on) {
+    if (dbg) {
       XP_CHECK(cudaMalloc(&rr.dbg, 8 * sizeof(unsigned long long)));
       XP_CHECK(cudaMemsetAsync(rr.dbg, 0, 8 * sizeof(unsigned long long), st));
     }
     XP_LAUNCH(k, (int)std::min<int64_t>(std::max<int64_t>(ceil_div(n_rows, kWsPairs * kWsGrab), 1), kNumSMs), 2 * kWsPairs * 32, smem, st, rr);
-    if (dbg_on) {
+    if (dbg) {
       unsigned long long h[8];
       XP_CHECK(cudaStreamSynchronize(st));
       XP_CHECK(cudaMemcpy(h, rr.dbg, sizeof h, cudaMemcpyDeviceToHost));
