@@ -200,7 +200,7 @@ class Explainer:
         if self.pathways is not None:
             sub_pathway_class = Pathways(sub_pathway, sub_pathway_names)
             if isinstance(sub_pathway[0][0], str):
-                sub_pathway_inds = sub_pathway_class.names2inds(sub_names)
+                sub_pathway_inds = sub_pathway_class.names2inds(sub_names, index=pathway_class.last_index, filtered=True)
             elif isinstance(sub_pathway[0][0], int):
                 sub_pathway_inds = sub_pathway
         del self.feat, self.edge_index  # explainer.py:476: the object is single use

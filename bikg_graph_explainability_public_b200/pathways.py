@@ -43,13 +43,15 @@ class Pathways:
         self.communities = communities
         self.community_names = community_names
         self.community_types = community_types
+        self.last_index = None
         if self.community_names is None:
             self.community_names = np.arange(len(self.communities)).tolist()
 
     def comp_graph(self, names):
         """pathways.py:33-102: keep communities with at least one member in the subgraph.
-        Members come back as the sorted unique *names* present in ``names`` (what ``intersect1d`` returns)."""
-        present = _first_index(names)
+        Members come back as the sorted unique *names* present in ``names`` (what ``intersect1d`` returns).
+        The name -> first-index map is kept in ``last_index`` so that ``names2inds`` on the result need not rebuild it."""
+        present = self.last_index = _first_index(names)
         sub, sub_names = [], []
         sub_types = [] if self.community_types is not None else None
         for i, (community, cname) in enumerate(zip(self.communities, self.community_names)):
@@ -63,11 +65,16 @@ class Pathways:
             sub_types = torch.tensor(sub_types, device=self.community_types.device)
         return sub, sub_names, sub_types
 
-    def names2inds(self, names):
-        """pathways.py:104-136: member names -> subgraph indices, in lexicographic name order."""
+    def names2inds(self, names, index=None, filtered=False):
+        """pathways.py:104-136: member names -> subgraph indices, in lexicographic name order.
+        ``index``: the name -> first-index map of ``names`` if the caller already has it (``comp_graph(...).last_index``);
+        ``filtered``: the communities are what ``comp_graph(names)`` returned (sorted unique names, all present), so the
+        per-community intersection is the identity and only the lookup remains.  Same result either way."""
         if isinstance(self.communities[0][0], int):
             return self.communities
-        first = _first_index(names)
+        first = _first_index(names) if index is None else index
+        if filtered:
+            return [[first[m] for m in community] for community in self.communities]
         inds = []
         for community in self.communities:
             common = sorted(first.keys() & set(_as_str(community)))

@@ -213,3 +213,7 @@ def test_name_resolution_fast_path_equals_intersect1d(case):
     assert sub == ref_sub
     assert len(sub_cnames) == len(sub) == 12
     assert Pathways(sub, sub_cnames).names2inds(sub_names) == ref_inds
+    # what Explainer.run does: reuse the index of comp_graph, skip the (identity) intersection of the filtered communities
+    pw = Pathways(communities, cnames)
+    sub2, sub_cnames2, _ = pw.comp_graph(sub_names)
+    assert Pathways(sub2, sub_cnames2).names2inds(sub_names, index=pw.last_index, filtered=True) == ref_inds
