@@ -46,6 +46,8 @@ _SIGNATURES = {
     "xpgnn_last_error": (C.c_char_p, []),
     "xpgnn_abi_version": (C.c_int, []),
     "xpgnn_launch_count": (i64, []),
+    "xpgnn_set_option": (C.c_int, [C.c_char_p, i32]),
+    "xpgnn_get_option": (C.c_int, [C.c_char_p, C.POINTER(i32)]),
     "xpgnn_mt19937_draw": (C.c_int, [ptr, ptr, ptr, i64, ptr]),
     "xpgnn_mask_max_draws": (i64, [ptr, ptr, ptr, i32, i32, i32]),
     "xpgnn_mask_resolve": (C.c_int, [C.POINTER(MaskPlan), ptr, ptr, ptr, i32, ptr, ptr]),
@@ -108,6 +110,17 @@ def stream_ptr():
     import torch
 
     return torch.cuda.current_stream().cuda_stream
+
+
+def set_options(**kv):
+    """Engine options (``xpgnn_set_option``); returns the previous values."""
+    lib, old = load(), {}
+    for k, v in kv.items():
+        prev = i32(0)
+        check(lib.xpgnn_get_option(k.encode(), C.byref(prev)))
+        old[k] = prev.value
+        check(lib.xpgnn_set_option(k.encode(), int(v)))
+    return old
 
 
 def launch_count():

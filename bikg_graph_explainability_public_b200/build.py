@@ -6,8 +6,11 @@ import sys
 _CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 
 
-def build(verbose=False, jobs=4):
-    proc = subprocess.run(["make", "-C", _CSRC, "-j%d" % jobs], capture_output=True, text=True)
+def build(verbose=False, jobs=8, force=False):
+    """``force``: recompile every translation unit (``make -B``) -- what ``__graft_entry__.build()`` does, so that a
+    successful build always means "these sources compile for sm_100a", not "object files were lying around"."""
+    cmd = ["make", "-C", _CSRC, "-j%d" % jobs] + (["-B"] if force else [])
+    proc = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or proc.returncode != 0:
         sys.stderr.write(proc.stdout[-4000:] + proc.stderr[-4000:])
     if proc.returncode != 0:

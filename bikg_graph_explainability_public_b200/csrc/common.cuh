@@ -7,6 +7,7 @@
 #include <atomic>
 #include <string>
 
+#include "knobs.cuh"
 #include "xpgnn_b200.h"
 
 namespace xpgnn {

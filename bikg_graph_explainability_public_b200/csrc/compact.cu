@@ -490,6 +490,211 @@ __global__ void __launch_bounds__(256) cspmm_long_kernel(const CspmmArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Segmented masked SpMM (layers >= 1, aggregate-first: unweighted sums of pre-scaled rows, out = scale * sum).
+//
+// The row-lockstep kernel above keeps ~1 gather instruction in flight per warp: every 4-row step is a chain of
+// dependent round trips (row ids -> list offsets -> source ids -> gathers -> self row), rows of unequal length
+// idle their lanes, and at 32 registers (8 CTAs / SM) it spills (r01 ncu: as many local as global load requests,
+// 111.6 GB through the L2 -> SM fabric for 97 GB of useful sectors).  Here a warp owns a block of 32 compact rows:
+//   * one coalesced load brings the block's row ids and list offsets, issued one block ahead of its use
+//     (the block index comes from the global in-order counter two blocks ahead);
+//   * the block's gather stream -- for GCN the row itself first (the operands of layers >= 1 are pre-scaled by
+//     deg^-1/2, so the unit self loop is one more unweighted term), then its active sources -- is staged in shared
+//     memory as words  id | row << 26 | last << 31 ;
+//   * the stream is cut into four equal contiguous pieces, one per group of 8 lanes (float4 each = one 128-byte row
+//     piece per group and gather), whatever the row lengths: a warp-level segmented sum.  Every lane keeps D gathers
+//     in flight through a rotating register queue; a word with the `last` bit closes its row: scale and store;
+//   * rows cut by a piece boundary are closed through shared memory in a fixed order (tail of the earlier piece, then
+//     the head of the later one), so the result does not depend on timing.
+// Rows with more than long_cnt active in-edges stay with cspmm_long_kernel.
+// ------------------------------------------------------------------------------------------
+constexpr int kSegCap = 256;  // stream positions staged per round (a 32-row block of C3 holds ~190)
+constexpr uint32_t kSegIdMask = (1u << kPackShift) - 1u;
+
+__device__ __forceinline__ float4 seg_gather(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void seg_store(float* p, const float4& acc, float sc) {
+  __stcs(reinterpret_cast<float4*>(p), make_float4(acc.x * sc, acc.y * sc, acc.z * sc, acc.w * sc));  // written once, read by the transform
+}
+
+template <int D, int OCC>
+__global__ void __launch_bounds__(128, OCC) cspmm_seg_kernel(const CspmmArgs a) {
+  constexpr int WARPS = 4;
+  __shared__ int s_start[33];
+  __shared__ int s_nact[32];
+  __shared__ __align__(16) uint32_t s_ids[WARPS][kSegCap];
+  __shared__ int s_rowv[WARPS][32];
+  __shared__ float s_rowscale[WARPS][32];
+  __shared__ int s_aend[WARPS][32];        // stream position one past the row's last entry
+  __shared__ uint32_t s_e[WARPS][32];      // first list entry of the row
+  __shared__ __align__(16) float s_head[WARPS][4][32];
+  __shared__ __align__(16) float s_tail[WARPS][4][32];
+  __shared__ __align__(16) float s_cr[WARPS][32];
+  __shared__ int s_headrow[WARPS][4];
+  __shared__ int s_next[WARPS][4];         // decoded item n + 1 (slot, chunk, first row)
+  if (threadIdx.x <= a.nb) s_start[threadIdx.x] = a.slot_tile_start[threadIdx.x];
+  if (threadIdx.x < a.nb) s_nact[threadIdx.x] = a.slot_info[threadIdx.x].x;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane & 7, grp = lane >> 3;
+  const int total = s_start[a.nb] * a.n_chunks * 4;  // items = 32-row blocks, ordered slot / chunk / 128-row tile / quarter
+  const bool gcn = a.kind == XPGNN_CONV_GCN;
+  uint32_t* ids = s_ids[warp];
+
+  // ---- two-deep item pipeline: item n is processed while the metadata loads of n + 1 and the counter fetch of n + 2 fly ----
+  int t_cur = 0;
+  auto grab = [&]() {
+    int it = 0;
+    if (lane == 0) it = atomicAdd(a.counter, 1);
+    return __shfl_sync(0xffffffffu, it, 0);
+  };
+  // decodes the item into s_next and issues the loads of its row ids / list offsets
+  auto load_meta = [&](int item, int& v, uint32_t& e, uint32_t& f) {
+    v = -1; e = 0; f = 0;
+    if (item >= total) return;
+    const int idx = item >> 2;
+    while (idx >= s_start[t_cur + 1] * a.n_chunks) ++t_cur;
+    const int ntb = s_start[t_cur + 1] - s_start[t_cur];
+    const int rem = idx - s_start[t_cur] * a.n_chunks;
+    const int c = rem / ntb;
+    const int row0 = (rem - c * ntb) * 128 + (item & 3) * 32;
+    if (lane == 0) { s_next[warp][0] = t_cur; s_next[warp][1] = c; }
+    const int i = row0 + lane;
+    if (i < s_nact[t_cur]) {
+      v = __ldcs(a.act_list + (int64_t)t_cur * a.N + i);
+      const uint32_t* rp = a.rowptr_c + (int64_t)t_cur * (a.N + 1) + i;
+      e = __ldcs(rp);
+      f = __ldcs(rp + 1);
+    }
+  };
+  int item1 = grab();
+  int v1;
+  uint32_t e1, f1;
+  load_meta(item1, v1, e1, f1);
+  int item2 = grab();
+
+  while (item1 < total) {
+    __syncwarp();
+    const int t = s_next[warp][0], c = s_next[warp][1];
+    __syncwarp();
+    {
+      const int v_l = v1;
+      const uint32_t e_l = e1, cnt_l = f1 - e1;
+      item1 = item2;
+      load_meta(item1, v1, e1, f1);   // consumed at the top of the next iteration
+      item2 = grab();
+      const bool valid = v_l >= 0;
+      const bool is_long = a.long_cnt > 0 && cnt_l > (uint32_t)a.long_cnt;
+      const int n_l = (valid && !is_long) ? (int)cnt_l + (gcn ? 1 : 0) : 0;
+      // inclusive prefix of the stream lengths
+      int a_end = n_l;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, a_end, o);
+        if (lane >= o) a_end += y;
+      }
+      s_rowv[warp][lane] = v_l;
+      s_rowscale[warp][lane] = gcn ? gcn_dinv(cnt_l) : 1.0f / (float)max(cnt_l, 1u);
+      s_aend[warp][lane] = a_end;
+      s_e[warp][lane] = e_l;
+      s_cr[warp][lane] = 0.0f;
+      // SAGE: a row without an active in-edge aggregates to zero and has no stream entry
+      uint32_t empties = __ballot_sync(0xffffffffu, valid && !is_long && n_l == 0);
+      while (empties) {
+        const int r = __ffs(empties) - 1;
+        empties &= empties - 1;
+        const int vr = __shfl_sync(0xffffffffu, v_l, r);
+        if (lane < 8)
+          __stcs(reinterpret_cast<float4*>(a.out + (int64_t)t * a.out_s_stride + (int64_t)c * a.out_chunk_stride + (int64_t)vr * 32 + lane * 4),
+                 make_float4(0.f, 0.f, 0.f, 0.f));
+      }
+    }
+    __syncwarp();
+    const int nA = s_aend[warp][31];
+    const int32_t* cc = a.ccol + a.slot_base[t];
+    const float* in_c = a.in + (int64_t)t * a.in_s_stride + (int64_t)c * a.in_chunk_stride + sub * 4;
+    float* out_c = a.out + (int64_t)t * a.out_s_stride + (int64_t)c * a.out_chunk_stride + sub * 4;
+
+    for (int S = 0; S < nA; S += kSegCap) {
+      const int len = min(kSegCap, nA - S);
+      // ---- stage the stream words of this round ----
+      for (int i = lane; i < len; i += 32) {
+        const int pos = S + i;
+        int r = 0;  // rows whose stream ends at or before pos
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1)
+          if (s_aend[warp][r + step - 1] <= pos) r += step;
+        const int ar = r ? s_aend[warp][r - 1] : 0;
+        int id;
+        if (gcn) id = pos == ar ? s_rowv[warp][r] : __ldcs(cc + s_e[warp][r] + (uint32_t)(pos - ar - 1));
+        else id = __ldcs(cc + s_e[warp][r] + (uint32_t)(pos - ar));
+        ids[i] = (uint32_t)id | ((uint32_t)r << kPackShift) | (pos == s_aend[warp][r] - 1 ? 0x80000000u : 0u);
+      }
+      __syncwarp();
+      // ---- stream: four contiguous pieces, D gathers in flight per lane ----
+      const int per = (len + 3) >> 2;
+      const int q1 = min((grp + 1) * per, len);
+      int q = min(grp * per, len);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      int headrow = -1;
+      float4 x[D];
+      uint32_t w[D];
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        w[k] = 0; x[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q + k < q1) {
+          w[k] = ids[q + k];
+          x[k] = seg_gather(in_c + (int64_t)(w[k] & kSegIdMask) * 32);
+        }
+      }
+      for (; q < q1; q += D) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          if (q + k < q1) {
+            const uint32_t wk = w[k];
+            acc.x += x[k].x; acc.y += x[k].y; acc.z += x[k].z; acc.w += x[k].w;
+            if (q + k + D < q1) {
+              w[k] = ids[q + k + D];
+              x[k] = seg_gather(in_c + (int64_t)(w[k] & kSegIdMask) * 32);
+            }
+            if (wk >> 31) {  // the row ends here
+              const int r = (wk >> kPackShift) & 31;
+              if (headrow < 0) {  // first row closed by this piece: it may have started in an earlier piece
+                headrow = r;
+                *reinterpret_cast<float4*>(&s_head[warp][grp][sub * 4]) = acc;
+              } else {
+                seg_store(out_c + (int64_t)s_rowv[warp][r] * 32, acc, s_rowscale[warp][r]);
+              }
+              acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+        }
+      }
+      // ---- close the rows cut by piece / round boundaries, in piece order ----
+      *reinterpret_cast<float4*>(&s_tail[warp][grp][sub * 4]) = acc;
+      if (sub == 0) s_headrow[warp][grp] = headrow;
+      __syncwarp();
+      float4 cy = *reinterpret_cast<const float4*>(&s_cr[warp][sub * 4]);  // open row carried in from the previous round
+      for (int h = 0; h < grp; ++h) {
+        const float4 tl = *reinterpret_cast<const float4*>(&s_tail[warp][h][sub * 4]);
+        if (s_headrow[warp][h] >= 0) cy = tl;
+        else { cy.x += tl.x; cy.y += tl.y; cy.z += tl.z; cy.w += tl.w; }
+      }
+      if (headrow >= 0) {
+        const float4 hd = *reinterpret_cast<const float4*>(&s_head[warp][grp][sub * 4]);
+        seg_store(out_c + (int64_t)s_rowv[warp][headrow] * 32, make_float4(cy.x + hd.x, cy.y + hd.y, cy.z + hd.z, cy.w + hd.w),
+                  s_rowscale[warp][headrow]);
+      }
+      __syncwarp();
+      if (grp == 3) {  // what stays open after the last piece goes to the next round
+        float4 co = acc;
+        if (headrow < 0) { co.x += cy.x; co.y += cy.y; co.z += cy.z; co.w += cy.w; }
+        *reinterpret_cast<float4*>(&s_cr[warp][sub * 4]) = co;
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // layers >= 1 of a HeteroConv(sum), transform-first: Z_r = H W_r^T has been computed per relation over the active
 // rows of its source type; this kernel gathers, per destination row, over the compacted lists of ALL relations into
 // the destination type, adds the merged root term and bias, applies the activation and writes the row ONCE
@@ -769,15 +974,10 @@ __global__ void __launch_bounds__(128) compact_head_kernel(const CHeadArgs a, in
 }
 
 // ------------------------------------------------------------------------------------------ host
-static bool compact_enabled() {
-  const char* e = getenv("XPGNN_COMPACT");
-  return !(e && std::string(e) == "0");
-}
+static bool compact_enabled() { return knobs().compact != 0; }
 
 static int compact_cw(const xpgnn_plan_t* p) {
-  const char* e = getenv("XPGNN_CW");
-  int cw = 32;
-  if (e && atoi(e) == 16) cw = 16;
+  int cw = knobs().cw == 16 ? 16 : 32;
   for (int l = 0; l < p->n_layers; ++l)
     if (p->layers_host[l].h_out % cw) cw = 16;
   return cw;
@@ -804,7 +1004,7 @@ static bool compact_act16(const xpgnn_plan_t* p) {
   if (p->precision != 2 || p->layers_host[0].rel_host[0].conv_kind != XPGNN_CONV_GCN) return false;
   for (int l = 0; l < p->n_layers; ++l)
     if (p->layers_host[l].h_out % 64 || p->layers_host[l].h_out > 256) return false;
-  return !(getenv("XPGNN_L0") && std::string(getenv("XPGNN_L0")) == "lists");
+  return !knobs().l0_lists;
 }
 
 struct CLayout {
@@ -874,8 +1074,22 @@ static CLayout compact_carve(const xpgnn_plan_t* p, void* ws, int64_t cap, int t
 int64_t compact_workspace_bytes(const xpgnn_plan_t* p, int tile) { return compact_carve(p, nullptr, 0, tile).bytes; }
 
 static int launch_cspmm(const CspmmArgs& a, int cw, cudaStream_t st) {
-  const int occ = getenv("XPGNN_OCC") ? atoi(getenv("XPGNN_OCC")) : 8;
+  const int occ = knobs().occ;
   void (*k)(const CspmmArgs);
+  // aggregate-first layers >= 1 (plain scaled sums over 32-float chunks): the segmented kernel
+  const int seg = knobs().seg;  // 0: row-lockstep kernel | 4 / 6 / 8: gathers in flight per lane
+  if (seg > 0 && cw == 32 && a.counter && !a.wgt && !a.addend && !a.bias && !a.layer0 && !a.prescale && a.act_fn == XPGNN_ACT_NONE) {
+    const int socc = knobs().seg_occ;
+    if (seg >= 8) k = socc == 8 ? cspmm_seg_kernel<8, 8> : cspmm_seg_kernel<8, 6>;
+    else if (seg >= 6) k = socc == 6 ? cspmm_seg_kernel<6, 6> : cspmm_seg_kernel<6, 8>;
+    else k = socc == 10 ? cspmm_seg_kernel<4, 10> : cspmm_seg_kernel<4, 8>;
+    int per_sm = 0;
+    XP_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, 128, 0));
+    ProfScope ps(a.prof_cat > 0 ? a.prof_cat : PROF_SPMM_TILE, st);
+    XP_LAUNCH(k, kNumSMs * std::max(per_sm, 1), 128, 0, st, a);
+    if (a.long_cnt > 0) XP_LAUNCH((cspmm_long_kernel<32, false>), kNumSMs * 8, 256, 0, st, a);
+    return 0;
+  }
   if (occ >= 8)
     k = cw == 32 ? (a.wgt ? cspmm_kernel<32, true, 8> : cspmm_kernel<32, false, 8>) : (a.wgt ? cspmm_kernel<16, true, 8> : cspmm_kernel<16, false, 8>);
   else
@@ -915,7 +1129,7 @@ int forward_compact(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32
   const xpgnn_layer_t& L0 = p->layers_host[0];
   XP_REQUIRE(L0.h_in == p->f_in, "layer 0 input width != feature width");
   // row-outer layer 0 (Z row-major) when a warp can own 128 columns; else the list-driven kernel (Z chunk-major)
-  const bool l0_lists = getenv("XPGNN_L0") && std::string(getenv("XPGNN_L0")) == "lists";
+  const bool l0_lists = knobs().l0_lists != 0;
   const bool l0_rows = !l0_lists && cw == 32 && L0.h_out % 64 == 0;
   const bool act16 = compact_act16(p) && l0_rows;   // bf16 activation storage
   const int64_t cstride16 = (int64_t)N * 64;        // chunk stride of the bf16 layout (elements)
@@ -934,9 +1148,9 @@ int forward_compact(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32
       if (launch_dense(rt, st, dense_prec)) return 1;
     }
   }
-  const int l2_stream = getenv("XPGNN_L2_STREAM") ? atoi(getenv("XPGNN_L2_STREAM")) : 1;
-  const int l2_gather = getenv("XPGNN_L2_GATHER") ? atoi(getenv("XPGNN_L2_GATHER")) : 0;
-  const bool dyn_sched = !(getenv("XPGNN_SCHED") && std::string(getenv("XPGNN_SCHED")) == "static");
+  const int l2_stream = knobs().l2_stream;
+  const int l2_gather = knobs().l2_gather;
+  const bool dyn_sched = !knobs().sched_static;
   XP_CHECK(cudaMemsetAsync(lay.keys + (int64_t)tile * N, 0, sizeof(unsigned long long), st));
   // hub rows get CTA-per-row variants of the row-per-warp kernels
   int n_long = 0;
@@ -945,7 +1159,7 @@ int forward_compact(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32
   XP_LAUNCH(find_long_rows_kernel, (int)ceil_div(N, 256), 256, 0, st, R0.rowptr, N, kLongRow, lay.long_rows, lay.n_long);
   XP_CHECK(cudaMemcpyAsync(&n_long, lay.n_long, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   XP_CHECK(cudaStreamSynchronize(st));
-  if (getenv("XPGNN_LONG") && std::string(getenv("XPGNN_LONG")) == "0") n_long = 0;
+  if (!knobs().long_rows) n_long = 0;
 
   const int w_first = s0 / 32, w_last = (s0 + n_s - 1) / 32;
   const int grid_rows = (int)std::min<int64_t>(std::max<int64_t>(ceil_div(N, 8), 1), (int64_t)kNumSMs * 8);
@@ -1023,7 +1237,7 @@ int forward_compact(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32
           s.out = lay.agg; s.out_chunk_stride = cstride16;
           {
             ProfScope ps(PROF_SPMM_TILE, st);
-            const int occ16 = getenv("XPGNN_OCC16") ? atoi(getenv("XPGNN_OCC16")) : 8;
+            const int occ16 = knobs().occ16;
             void (*k16)(const CspmmArgs) = occ16 >= 8 ? cspmm16_kernel<8> : (occ16 <= 4 ? cspmm16_kernel<4> : cspmm16_kernel<6>);
             int per_sm = 0;
             XP_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k16, 256, 0));
@@ -1193,7 +1407,7 @@ struct HLayout {
 static bool same_dst(const xpgnn_relation_t& a, const xpgnn_relation_t& b) { return a.dst_lo == b.dst_lo && a.dst_hi == b.dst_hi; }
 
 bool compact_hetero_eligible(const xpgnn_plan_t* p) {
-  if (!compact_enabled() || (getenv("XPGNN_COMPACT_HETERO") && std::string(getenv("XPGNN_COMPACT_HETERO")) == "0")) return false;
+  if (!compact_enabled() || !knobs().compact_hetero) return false;
   if (p->prune || p->n_layers < 1 || p->n_layers > kMaxConvIso || p->n_head > kMaxHeadC || p->n_nodes >= (1 << kPackShift)) return false;
   if (p->precision == 2) return false;  // bf16 storage cannot accumulate relation by relation
   int n_self = 0;
@@ -1414,7 +1628,7 @@ int forward_compact_hetero(const xpgnn_plan_t* p, const uint32_t* act, int32_t W
     for (size_t i = 0; i < lay.csr.size(); ++i)
       XP_CHECK(cudaMemcpyAsync(&nl[i], lay.csr[i].n_long_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     XP_CHECK(cudaStreamSynchronize(st));
-    const bool off = getenv("XPGNN_LONG") && std::string(getenv("XPGNN_LONG")) == "0";
+    const bool off = !knobs().long_rows;
     for (size_t i = 0; i < lay.csr.size(); ++i) lay.csr[i].n_long = off ? 0 : nl[i];
   }
 
@@ -1460,7 +1674,7 @@ int forward_compact_hetero(const xpgnn_plan_t* p, const uint32_t* act, int32_t W
       for (int l = 0; l < NL; ++l) {
         const xpgnn_layer_t& L = p->layers_host[l];
         // layer 0, one pass per destination type over all of its incoming relations (no hub rows, <= kMaxL0Rel relations)
-        bool multi_l0 = l == 0 && !(getenv("XPGNN_L0_MULTI") && std::string(getenv("XPGNN_L0_MULTI")) == "0");
+        bool multi_l0 = l == 0 && knobs().l0_multi != 0;
         if (multi_l0) {
           for (auto& c : lay.csr) multi_l0 = multi_l0 && c.n_long == 0;
           for (int r = 0; r < L.n_rel && multi_l0; ++r) {
@@ -1490,7 +1704,7 @@ int forward_compact_hetero(const xpgnn_plan_t* p, const uint32_t* act, int32_t W
         }
         // layers >= 1 transform-first: Z_q = H W_q^T per relation over the active rows of its source type, then one gather
         // pass per destination type over all of its relations (no hub rows, <= kMaxL0Rel relations per type)
-        bool multi_l1 = l > 0 && getenv("XPGNN_L1_MULTI") && std::string(getenv("XPGNN_L1_MULTI")) == "1";  // opt-in: measured slower on C4 (200 vs 224 evals/s)
+        bool multi_l1 = l > 0 && knobs().l1_multi == 1;  // opt-in: measured slower on C4 (200 vs 224 evals/s)
         if (multi_l1) {
           for (auto& c : lay.csr) multi_l1 = multi_l1 && c.n_long == 0;
           for (int r = 0; r < L.n_rel && multi_l1; ++r) {

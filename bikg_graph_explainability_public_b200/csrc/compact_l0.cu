@@ -1026,12 +1026,16 @@ int launch_l0_rows(const L0RowsArgs& r, bool sigmoid, bool out16, int n_rows, cu
   // XPGNN_L0_WS: 1 (default) warp specialised, column-block tiling; 2 warp specialised, slot x column tiling (widths % 128 == 0:
   // 40 % fewer shared-memory wavefronts and fewer cycles, but a lower clock under the power cap -- 6.2 against 5.3 ms at C3);
   // 0 one warp per row.  Read per call so that the tests can compare the three.
-  const int ws_env = getenv("XPGNN_L0_WS") ? atoi(getenv("XPGNN_L0_WS")) : 1;
+  const int ws_env = knobs().l0_ws;
   int ws = (int64_t)r.N * r.h0 < (int64_t(1) << 31) ? ws_env : 0;  // 32-bit source-row offsets in the producers
   if (ws == 2 && (r.h0 % 128 != 0 || r.rows)) ws = 1;  // the slot x column kernel takes whole ranges only
   const bool plain = !r.accumulate && r.finish;
   if (ws) {
+#ifdef XPGNN_EXPERIMENTS
     static const bool dbg_on = getenv("XPGNN_L0_DBG") != nullptr;  // cycle counters; synchronises; diagnostics only (fp32, ReLU / none)
+#else
+    constexpr bool dbg_on = false;
+#endif
     const bool dbg = dbg_on && !out16 && plain && !sigmoid;
     void (*k)(const L0RowsArgs);
     if (ws == 2)

@@ -27,6 +27,13 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+// ablation switches of the round-1 analysis (skip stores / loads / MMAs): compiled in only with -DXPGNN_EXPERIMENTS, so
+// that no environment variable can make the shipped kernel skip work
+#ifdef XPGNN_EXPERIMENTS
+#define XP_EXP(a, bit) ((a).exp_flags & (bit))
+#else
+#define XP_EXP(a, bit) false
+#endif
 __constant__ int g_backoff_after = 16;  // failed polls before a waiting thread starts sleeping (XPGNN_DENSE_BACKOFF)
 
 template <bool BACKOFF = true>
@@ -319,8 +326,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const DenseArgs
         const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-          buf[2 * p] = (ld_row[p] && !(a.exp_flags & 2)) ? __ldg(reinterpret_cast<const float4*>(ld_row[p] + o0)) : zero;
-          buf[2 * p + 1] = (ld_row[p] && !(a.exp_flags & 2)) ? __ldg(reinterpret_cast<const float4*>(ld_row[p] + o1)) : zero;
+          buf[2 * p] = (ld_row[p] && !XP_EXP(a, 2)) ? __ldg(reinterpret_cast<const float4*>(ld_row[p] + o0)) : zero;
+          buf[2 * p + 1] = (ld_row[p] && !XP_EXP(a, 2)) ? __ldg(reinterpret_cast<const float4*>(ld_row[p] + o1)) : zero;
         }
       }
       if (a.rows_packed && nxt_ti != ti + 1 && ti + 1 < my_tiles) {  // table entries of the next tile, in flight with the data
@@ -392,7 +399,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const DenseArgs
             const uint64_t da_hi = smem_desc(a_hi + a_off, 128, Cfg::K16 * 128);
             const uint64_t db_hi = smem_desc(sB_addr + b_off, 128, kb16 * 128);
             const uint32_t first = (kc == 0 && ks == 0) ? 0u : 1u;
-            if (a.exp_flags & 4) continue;
+            if (XP_EXP(a, 4)) continue;
             umma<MODE>(d_tmem, da_hi, db_hi, idesc, first);
             if (MODE == 0) {
               const uint64_t da_lo = smem_desc(a_lo + a_off, 128, Cfg::K16 * 128);
@@ -495,7 +502,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const DenseArgs
               }
               v[i].x *= rs_r[i]; v[i].y *= rs_r[i]; v[i].z *= rs_r[i]; v[i].w *= rs_r[i];
             }
-            if (a.exp_flags & 1) {
+            if (XP_EXP(a, 1)) {
             } else if (a.out16) {
               __nv_bfloat16* out16 = reinterpret_cast<__nv_bfloat16*>(a.out);
 #pragma unroll
@@ -551,11 +558,15 @@ static bool tc_eligible(const DenseArgs& d, int mode) {
 
 int launch_dense_tc(const DenseArgs& d_in, int mode, cudaStream_t st) {
   DenseArgs d = d_in;
+#ifdef XPGNN_EXPERIMENTS  // ablation build only (make EXPERIMENTS=1): never in the shipped library
   if (const char* e = getenv("XPGNN_DENSE_EXP")) d.exp_flags = atoi(e);
   if (const char* e = getenv("XPGNN_DENSE_BACKOFF")) {
     const int v = atoi(e);
     XP_CHECK(cudaMemcpyToSymbolAsync(g_backoff_after, &v, sizeof(int), 0, cudaMemcpyHostToDevice, st));
   }
+#else
+  d.exp_flags = 0;
+#endif
   XP_REQUIRE(tc_eligible(d, mode), "shape not eligible for the tensor-core dense path");
   const int n_pad = (d.n_out + 15) / 16 * 16;
   uint32_t cols = 32;
@@ -565,7 +576,11 @@ int launch_dense_tc(const DenseArgs& d_in, int mode, cudaStream_t st) {
   const int64_t tiles = ceil_div(d.M, TM);
   const int grid = (int)std::min<int64_t>(tiles, kNumSMs);
   // XPGNN_DENSE_DBG=1: per-role cycle counters of CTA 0 (synchronises; diagnostics only)
+#ifdef XPGNN_EXPERIMENTS
   static const bool dbg_on = getenv("XPGNN_DENSE_DBG") != nullptr;
+#else
+  constexpr bool dbg_on = false;
+#endif
   unsigned long long* dbg = nullptr;
   if (dbg_on) {
     XP_CHECK(cudaMalloc(&dbg, 8 * sizeof(unsigned long long)));

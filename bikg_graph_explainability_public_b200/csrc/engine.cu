@@ -675,9 +675,7 @@ int xpgnn_forward(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32_t
   XP_REQUIRE(p->n_head <= kMaxHead, "head deeper than 8 layers");
   XP_REQUIRE(p->precision >= 0 && p->precision <= 2, "plan precision must be 0 (fp32), 1 (bf16 transforms) or 2 (bf16 transforms + bf16 activation storage)");
   // fp32 plans use the 3xTF32 tensor-core transform (error ~2^-20) unless XPGNN_DENSE=simt forces exact FMA
-  const char* dense_env = getenv("XPGNN_DENSE");
-  const int dense_prec = p->precision >= 1 ? DENSE_TC_BF16
-                                           : ((dense_env && std::string(dense_env) == "simt") ? DENSE_SIMT : DENSE_TC_TF32X3);
+  const int dense_prec = p->precision >= 1 ? DENSE_TC_BF16 : (knobs().dense_simt ? DENSE_SIMT : DENSE_TC_TF32X3);
   XP_REQUIRE(!p->prune || p->hop, "prune = 1 needs the hop levels");
   if (n_s == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
@@ -725,7 +723,7 @@ int xpgnn_forward(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32_t
   // ---- coalition-invariant part of layer 0: Z_r = X W_r^T, R0 = sum_r (b_r + X W_root,r^T) ----
   const xpgnn_layer_t& L0 = p->layers_host[0];
   // pruned homogeneous stacks run layer 0 through the row-outer kernels of compact_l0.cu (see the layer loop)
-  const bool prune_l0_env = !(getenv("XPGNN_PRUNE_L0") && std::string(getenv("XPGNN_PRUNE_L0")) == "0");
+  const bool prune_l0_env = knobs().prune_l0 != 0;
   const bool prune_l0 = prune_l0_env && p->prune && NL > 1 && L0.n_rel == 1 && L0.rel_host[0].src_lo == 0 && L0.rel_host[0].src_hi == N &&
                         L0.rel_host[0].dst_lo == 0 && L0.rel_host[0].dst_hi == N && L0.h_out % 64 == 0 &&
                         (int64_t)N * L0.h_out < (int64_t(1) << 31) && n_rows[0] > n_rows[1];
@@ -768,12 +766,11 @@ int xpgnn_forward(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32_t
   };
 
   // ---- fused SpMM + tcgen05 transform for layers >= 1 (single relation per destination range, no row list) ----
-  const char* fused_env = getenv("XPGNN_FUSED");
+
   // opt-in (XPGNN_FUSED=1): at one 512-thread CTA per SM its gather / MMA / epilogue phases do not overlap and it
   // measured 49.7 ms per C3 tile against 23.1 + 18.8 ms for the unfused pair (profiles/r01_summary.md)
-  const bool fused_on = dense_prec == DENSE_TC_TF32X3 && !p->prune && fused_env && std::string(fused_env) == "1";
-  const char* sb_env = getenv("XPGNN_FUSED_SB");
-  const int fused_sb = sb_env ? atoi(sb_env) : 0;
+  const bool fused_on = dense_prec == DENSE_TC_TF32X3 && !p->prune && knobs().fused == 1;
+  const int fused_sb = knobs().fused_sb;
   std::vector<std::vector<char>> use_fused(NL);
   for (int l = 1; l < NL; ++l) {
     const xpgnn_layer_t& L = p->layers_host[l];

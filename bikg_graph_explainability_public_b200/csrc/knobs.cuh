@@ -1,0 +1,36 @@
+// Engine knobs.  Every XPGNN_* environment variable is read ONCE, at the first use of the library; after that a knob
+// changes only through xpgnn_set_option (include/xpgnn_b200.h) -- which is how the tests and the sweep tools compare
+// kernel variants in one process.  All knobs select between implementations that compute the same function; nothing here
+// skips work (the experiment switches of round 1 -- XPGNN_DENSE_EXP and friends -- are compiled out, see dense_tc.cu).
+#pragma once
+#include <stdint.h>
+
+namespace xpgnn {
+
+struct Knobs {
+  int compact = 1;         // XPGNN_COMPACT: compact path for homogeneous stacks in full mode
+  int compact_hetero = 1;  // XPGNN_COMPACT_HETERO
+  int cw = 32;             // XPGNN_CW: 32 | 16 floats per activation chunk
+  int l0_lists = 0;        // XPGNN_L0=lists: list-driven layer 0 instead of the row-outer kernels
+  int occ = 8;             // XPGNN_OCC: CTAs / SM of the row-lockstep SpMM
+  int seg = 4;             // XPGNN_SEG: 0 row-lockstep SpMM | 4 / 6 / 8 segmented SpMM with that many gathers in flight per lane
+  int seg_occ = 0;         // XPGNN_SEG_OCC: 0 default CTAs / SM of the chosen segmented variant
+  int l2_stream = 1;       // XPGNN_L2_STREAM / XPGNN_L2_GATHER: L2 eviction priority of streamed / gathered accesses
+  int l2_gather = 0;
+  int sched_static = 0;    // XPGNN_SCHED=static: static round-robin instead of the in-order work counter
+  int long_rows = 1;       // XPGNN_LONG=0: hub rows through the row-per-warp kernels
+  int occ16 = 8;           // XPGNN_OCC16
+  int l0_multi = 1;        // XPGNN_L0_MULTI
+  int l1_multi = 0;        // XPGNN_L1_MULTI
+  int l0_ws = 1;           // XPGNN_L0_WS: 0 one warp per row | 1 warp specialised | 2 slot x column tiling
+  int dense_simt = 0;      // XPGNN_DENSE=simt: exact fp32 FMA transforms instead of 3xTF32 tensor-core products
+  int prune_l0 = 1;        // XPGNN_PRUNE_L0
+  int fused = 0;           // XPGNN_FUSED
+  int fused_sb = 0;        // XPGNN_FUSED_SB
+};
+
+Knobs& knobs();                               // first call reads the environment
+int set_knob(const char* name, int value);    // 0 ok, 1 unknown name
+int get_knob(const char* name, int* value);
+
+}  // namespace xpgnn

@@ -5,10 +5,68 @@
 //   :262-397 (mask_generator) and pathways.py:234-385 of the reference.
 // The (rows x N) bool matrix of the reference is never needed by the engine: bits are emitted
 // directly in the packed node-major layout the masked SpMM reads (act[v][w]).
+#include <cstdlib>
+
 #include "common.cuh"
+#include "knobs.cuh"
 
 namespace xpgnn {
 thread_local std::string g_last_error;
+
+namespace {
+struct KnobEntry { const char* name; int Knobs::*field; };
+const KnobEntry kKnobTable[] = {
+    {"compact", &Knobs::compact}, {"compact_hetero", &Knobs::compact_hetero}, {"cw", &Knobs::cw}, {"l0_lists", &Knobs::l0_lists},
+    {"occ", &Knobs::occ}, {"seg", &Knobs::seg}, {"seg_occ", &Knobs::seg_occ}, {"l2_stream", &Knobs::l2_stream},
+    {"l2_gather", &Knobs::l2_gather}, {"sched_static", &Knobs::sched_static}, {"long_rows", &Knobs::long_rows}, {"occ16", &Knobs::occ16},
+    {"l0_multi", &Knobs::l0_multi}, {"l1_multi", &Knobs::l1_multi}, {"l0_ws", &Knobs::l0_ws}, {"dense_simt", &Knobs::dense_simt},
+    {"prune_l0", &Knobs::prune_l0}, {"fused", &Knobs::fused}, {"fused_sb", &Knobs::fused_sb}};
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e && *e ? atoi(e) : dflt;
+}
+bool env_is(const char* name, const char* value) {
+  const char* e = getenv(name);
+  return e && std::string(e) == value;
+}
+}  // namespace
+
+Knobs& knobs() {
+  static Knobs k = [] {
+    Knobs d;
+    d.compact = env_int("XPGNN_COMPACT", d.compact);
+    d.compact_hetero = env_int("XPGNN_COMPACT_HETERO", d.compact_hetero);
+    d.cw = env_int("XPGNN_CW", d.cw) == 16 ? 16 : 32;
+    d.l0_lists = env_is("XPGNN_L0", "lists");
+    d.occ = env_int("XPGNN_OCC", d.occ);
+    d.seg = env_int("XPGNN_SEG", d.seg);
+    d.seg_occ = env_int("XPGNN_SEG_OCC", d.seg_occ);
+    d.l2_stream = env_int("XPGNN_L2_STREAM", d.l2_stream);
+    d.l2_gather = env_int("XPGNN_L2_GATHER", d.l2_gather);
+    d.sched_static = env_is("XPGNN_SCHED", "static");
+    d.long_rows = env_int("XPGNN_LONG", d.long_rows);
+    d.occ16 = env_int("XPGNN_OCC16", d.occ16);
+    d.l0_multi = env_int("XPGNN_L0_MULTI", d.l0_multi);
+    d.l1_multi = env_int("XPGNN_L1_MULTI", d.l1_multi);
+    d.l0_ws = env_int("XPGNN_L0_WS", d.l0_ws);
+    d.dense_simt = env_is("XPGNN_DENSE", "simt");
+    d.prune_l0 = env_int("XPGNN_PRUNE_L0", d.prune_l0);
+    d.fused = env_int("XPGNN_FUSED", d.fused);
+    d.fused_sb = env_int("XPGNN_FUSED_SB", d.fused_sb);
+    return d;
+  }();
+  return k;
+}
+int set_knob(const char* name, int value) {
+  for (const KnobEntry& e : kKnobTable)
+    if (std::string(e.name) == name) { knobs().*(e.field) = value; return 0; }
+  return 1;
+}
+int get_knob(const char* name, int* value) {
+  for (const KnobEntry& e : kKnobTable)
+    if (std::string(e.name) == name) { *value = knobs().*(e.field); return 0; }
+  return 1;
+}
 std::atomic<int64_t> g_launches{0};
 
 // ------------------------------------------------------------------------------------------
@@ -302,6 +360,16 @@ extern "C" {
 
 const char* xpgnn_last_error(void) { return g_last_error.c_str(); }
 int xpgnn_abi_version(void) { return XPGNN_ABI_VERSION; }
+int xpgnn_set_option(const char* name, int32_t value) {
+  XP_REQUIRE(name && set_knob(name, value) == 0, "unknown engine option");
+  return 0;
+}
+int xpgnn_get_option(const char* name, int32_t* value) {
+  int v = 0;
+  XP_REQUIRE(name && value && get_knob(name, &v) == 0, "unknown engine option");
+  *value = v;
+  return 0;
+}
 int64_t xpgnn_launch_count(void) { return g_launches.load(); }
 
 int xpgnn_mt19937_draw(uint32_t* state624, int32_t* pos, uint32_t* draws, int64_t n, void* stream) {

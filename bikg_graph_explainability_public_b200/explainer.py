@@ -38,13 +38,16 @@ def set_seed(seed=100):
 
 def build_engine(feat, edge_index, arch, element_index, node_type=None, edge_type=None, node_type_names=None,
                  edge_type_names=None, padded_dims=None, out_type=None, hop=None, prune=False, precision="fp32",
-                 query_flat=None):
+                 query_flat=None, model=None, queries=None):
     """Lower ``arch`` and bind it to the (flattened) computational graph.
 
     ``element_index`` follows the reference: the row of the model output that is read
-    (``model.py:247,325``), i.e. an index *inside the output node type* for hetero graphs."""
+    (``model.py:247,325``), i.e. an index *inside the output node type* for hetero graphs.
+    ``model``: an already lowered plan (``lowering.lower_candidates``); ``queries``: flat node ids to read instead of
+    the single element (probe check)."""
     dev = require_cuda()
-    model = lower(arch)
+    if model is None:
+        model = lower(arch)
     n = int(feat.shape[0])
     if node_type_names is None:
         if model.hetero:
@@ -71,17 +74,141 @@ def build_engine(feat, edge_index, arch, element_index, node_type=None, edge_typ
     if model.out_dim != 1:
         raise NotImplementedError("the surrogate needs a scalar prediction per node (model output width 1)")
     multi = n_types >= 2
-    eng = MaskedForward(graph, model, [q], prune=prune and hop is not None, hop=hop, zero_edge_rule=multi,
-                        precision=precision)
+    eng = MaskedForward(graph, model, [q] if queries is None else list(queries), prune=prune and hop is not None, hop=hop,
+                        zero_edge_rule=multi and queries is None, precision=precision)
     # (B,1) targets broadcast against (B,) predictions in the reference loss (wlm.py:517); the
     # multi-node-type branch yields (B,) targets (model.py:251) and the plain weighted MSE
     eng.broadcast_y = not multi
     return eng
 
 
+def _forward_arity(arch):
+    import inspect
+
+    return len(inspect.getfullargspec(arch.forward).args)  # model.py:104: 3 = (self, x, edge_index), 5 = + node / edge types
+
+
+def verify_lowering(arch, feat_dims, node_type_names=None, edge_type_names=None, out_type=None, seed=12345):
+    """Pick the lowered plan that IS ``arch``: the reference calls ``arch(feat, edge_index)`` as a black box
+    (``model.py:104-112``), the engine runs a lowered plan, so every candidate plan (``lowering.lower_candidates``) is
+    evaluated by the engine on a small random probe graph with no node removed and compared with ``arch`` itself on the
+    same graph, all output rows.  Returns ``(plan, status)``, status = "verified" or "unverified: ..." when ``arch``
+    cannot be called (weight containers of ``nn.py``: their plan is their definition).  Raises ``NotImplementedError``
+    when no candidate reproduces ``arch`` -- a model with skip connections, functional ops the lowering does not know, or
+    layers applied in an order the plan does not reflect must not be explained with a different function."""
+    from .lowering import lower_candidates
+
+    cands = lower_candidates(arch)
+    g = torch.Generator().manual_seed(seed)
+    par = next(arch.parameters(), None)
+    adev = par.device if par is not None else torch.device("cpu")
+    hetero = node_type_names is not None
+    if not hetero:
+        n, e = 48, 220
+        x = torch.randn(n, int(feat_dims), generator=g)
+        ei = torch.randint(0, n, (2, e), generator=g)
+        ei = torch.cat([ei, ei[:, :7], torch.arange(5).repeat(2, 1)], 1)  # duplicate edges and self loops
+        args = (x.to(adev), ei.to(adev))
+        if _forward_arity(arch) == 5:
+            args = args + (torch.zeros(n, device=adev), torch.zeros(ei.shape[1], device=adev))
+    else:
+        counts = [20 + 3 * i for i in range(len(node_type_names))]
+        x_dict = {t: torch.randn(c, int(feat_dims[t]), generator=g) for t, c in zip(node_type_names, counts)}
+        ei_dict = {}
+        for r in edge_type_names:
+            r = tuple(r)
+            ns, nd = counts[node_type_names.index(r[0])], counts[node_type_names.index(r[-1])]
+            ei_dict[r] = torch.stack([torch.randint(0, ns, (60,), generator=g), torch.randint(0, nd, (60,), generator=g)])
+        args = ({t: v.to(adev) for t, v in x_dict.items()}, {r: v.to(adev) for r, v in ei_dict.items()})
+    was_training = arch.training
+    arch.eval()
+    try:
+        with torch.no_grad():
+            ref = arch(*args)
+    except NotImplementedError as ex:
+        if "weight container" in str(ex) or "layers are weight containers" in str(ex):
+            return cands[-1], "unverified: arch is built from weight containers (nn.py), its plan is its definition"
+        raise
+    finally:
+        arch.train(was_training)
+    # rows of the reference output <-> flat probe node ids
+    if hetero:
+        raw = Data(x_dict, ei_dict)
+        ntn, etn, feat, ei, node_types, edge_types, nptr, _eptr, pads = raw.preprocess_hetero_graph()
+        if isinstance(ref, dict):  # model.py:255-292: outputs of the node types, stacked in dict order
+            rows, flat = [], []
+            for t, v in ref.items():
+                rows.append(v)
+                lo = nptr[ntn.index(t)]
+                flat += list(range(lo, lo + v.shape[0]))
+            ref = torch.vstack(rows)
+        else:
+            t = out_type if out_type is not None else getattr(arch, "out_type", None) or ntn[0]
+            lo = nptr[ntn.index(t)]
+            flat = list(range(lo, lo + ref.shape[0]))
+    else:
+        ntn = etn = node_types = edge_types = pads = None
+        feat, ei = x, ei
+        flat = list(range(ref.shape[0]))
+    ref = ref.detach().float().cpu().reshape(len(flat), -1)[:, 0].numpy()
+    dev = require_cuda()
+    act = torch.ones((int(feat.shape[0]), 1), dtype=torch.int32, device=dev)
+    worst = []
+    for cand in cands:
+        try:
+            eng = build_engine(feat.to(dev), ei.to(dev), arch, 0, node_types, edge_types, ntn, etn, pads, out_type=out_type,
+                               model=cand, queries=flat)
+        except NotImplementedError as ex:
+            worst.append("%s: %s" % (cand.how, ex))
+            continue
+        y = eng(act, 1)[0].cpu().numpy()
+        err = float(np.max(np.abs(y - ref) / np.maximum(np.abs(ref), 1e-3)))
+        if err <= 2e-4:
+            return cand, "verified"
+        worst.append("%s: max rel. deviation %.3g on the probe graph" % (cand.how, err))
+    raise NotImplementedError(
+        "arch.forward is not the layer sequence the engine can lower (%s); supported: chains of GCNConv / SAGEConv(mean) / "
+        "HeteroConv(sum) with ReLU / Sigmoid, then Linear layers" % "; ".join(worst))
+
+
+def sync_rng_across_ranks():
+    """One process per GPU: every rank replays the coalition stream of the CPU generator, so the generators must agree.
+    ``set_seed`` guarantees that only for ``times == 1`` (explainer.py:342); rank 0's state is made authoritative."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    box = [torch.get_rng_state()]
+    dist.broadcast_object_list(box, src=0)
+    torch.set_rng_state(box[0])
+
+
+def check_ranks_agree(act):
+    """Ranks evaluate slices of ONE coalition matrix; raise if theirs differ (mismatched masks would pair predictions
+    with the wrong rows and the replicated fit would silently train on wrong targets)."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    a = act.view(-1)
+    n = int(a.numel())
+    wcol = (torch.arange(int(act.shape[1]), device=act.device, dtype=torch.int64) % 8191) + 1
+    h = torch.stack([torch.sum(a, dtype=torch.int64), torch.sum(torch.sum(act, dim=0, dtype=torch.int64) * wcol),
+                     torch.sum(act[:: max(n // (1 << 20) // max(int(act.shape[1]), 1), 1)].to(torch.int64) * 31 % 1000003),
+                     torch.tensor(n, device=act.device, dtype=torch.int64)])
+    lo, hi = h.clone(), h.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    if not torch.equal(lo, hi):
+        raise RuntimeError("ranks generated different coalition masks (per-rank seeding?): Explainer.run needs the same "
+                           "global CPU generator state on every rank")
+
+
 class Explainer:
-    #: engine knobs (extension; defaults give reference-identical results)
-    engine_options = dict(prune=True, precision="fp32")
+    #: engine knobs (extension).  precision "fp32": fp32 storage and accumulation, dense transforms as 3xTF32 tensor-core
+    #: products (error ~1e-6 relative, inside the 1e-4 bar); "bf16" / "bf16_act": the 2e-2 bar.  verify: compare the
+    #: lowered plan with ``arch`` itself on a probe graph before explaining (see ``verify_lowering``).
+    engine_options = dict(prune=True, precision="fp32", verify=True)
 
     def __init__(self, feat, edge_index, arch, params, names, pathways=None, pathway_names=None, element_type=None,
                  problem="node_prediction", node_types=None, edge_types=None):
@@ -208,24 +335,46 @@ class Explainer:
         elements = int(sub_feat.shape[0])
         opts = dict(type(self).engine_options)
         opts.update(getattr(self, "options", {}))
-        engine = build_engine(sub_feat, sub_ei, self.arch, int(sub_ind[0]), sub_nt, sub_et, ntn, etn, pads,
-                              out_type=self.element_type if isinstance(self.element_type, str) else None,
-                              hop=hop, prune=opts["prune"], precision=opts["precision"], query_flat=query_flat)
+        out_type = self.element_type if isinstance(self.element_type, str) else None
         self.arch.eval()
-        config_vals = []
+        plan = None
+        self.lowering_status = "not checked"
+        if opts.get("verify", True):  # the plan must be the function the reference would call (model.py:104-112)
+            fd = int(sub_feat.shape[1]) if ntn is None else {t: int(sub_feat.shape[1]) - int(pads[i]) for i, t in enumerate(ntn)}
+            plan, self.lowering_status = verify_lowering(self.arch, fd, ntn, etn, out_type)
+        engine = build_engine(sub_feat, sub_ei, self.arch, int(sub_ind[0]), sub_nt, sub_et, ntn, etn, pads,
+                              out_type=out_type, hop=hop, prune=opts["prune"], precision=opts["precision"],
+                              query_flat=query_flat, model=plan)
+        # ---- all repeats' coalitions first: the masks, the surrogate init and the DataLoader seed draw of repeat r + 1
+        # depend on the RNG stream only (masks -> randperm -> N init draws -> 2 draws, explainer.py:490-523 / wlm.py:210),
+        # never on the predictions, so every repeat's rows go through ONE sharded engine call ----
+        sync_rng_across_ranks()
+        sets = []
         for _ in range(times):
             coalitions, _rows = Mask(sub_feat, sub_ei, sub_pathway_inds, self.params, self.problem).mask_generator()
             wlrm = LinearRegression(elements)           # kaiming-uniform init: next N draws of the CPU stream
             torch.empty((), dtype=torch.int64).random_()  # iter(DataLoader) base seed (wlm.py:210)
-            y = sharded_eval(engine, coalitions.act, coalitions.n_coalitions)[:, 0]
+            sets.append((coalitions, wlrm.layer.weight.detach().reshape(-1)))
+        if times == 1:
+            act_all, n_all = sets[0][0].act, sets[0][0].n_coalitions
+        else:  # repeats side by side along the word axis; a repeat's last word is padded with all-off rows
+            act_all = torch.cat([c.act for c, _ in sets], dim=1).contiguous()
+            n_all = 32 * int(act_all.shape[1])
+        check_ranks_agree(act_all)
+        y_all = sharded_eval(engine, act_all, n_all)[:, 0]
+        config_vals, word0 = [], 0
+        for coalitions, w0 in sets:
+            y = y_all[32 * word0: 32 * word0 + coalitions.n_coalitions]
+            word0 += coalitions.words
             kern = shap_weights(coalitions.popcount, elements, coalitions.batch_size)
-            w, losses = fit_surrogate(coalitions, y, kern, wlrm.layer.weight.detach().reshape(-1), self.params,
-                                      broadcast_y=engine.broadcast_y, want_losses=False)
+            w, losses = fit_surrogate(coalitions, y, kern, w0, self.params, broadcast_y=engine.broadcast_y, want_losses=False)
             config_vals.append(w)
             self.last_stats = dict(n_sub=elements, e_sub=int(sub_ei.shape[1]), coalitions=coalitions.n_coalitions,
-                                   batch_size=coalitions.batch_size, tile_coalitions=engine.tile_coalitions)
-            self._last = dict(coalitions=coalitions, y=y, kernel=kern, w0=wlrm.layer.weight.detach().reshape(-1),
-                              subset_names=sub_names, sub_edge_index=sub_ei, sub_ind=query_flat)
+                                   batch_size=coalitions.batch_size, tile_coalitions=engine.tile_coalitions,
+                                   repeats_per_engine_call=times, lowering=self.lowering_status)
+            if opts.get("keep_last", False):  # tests / debugging only: pins the coalition draws and predictions in HBM
+                self._last = dict(coalitions=coalitions, y=y, kernel=kern, w0=w0, subset_names=sub_names,
+                                  sub_edge_index=sub_ei, sub_ind=query_flat)
         mean, std = self.weight_stacking(config_vals)
         config_val_df = Data.config_val_dataframe(mean, std, sub_names)
         pathway_df = None

@@ -33,6 +33,16 @@ int xpgnn_abi_version(void);
 /* number of kernel launches issued by this library since load (bench.py `gpu_launches`) */
 int64_t xpgnn_launch_count(void);
 
+/* Engine options.  Every option selects between implementations of the same function (kernel variant, occupancy, path
+ * selection); none changes what is computed beyond floating-point summation order.  The XPGNN_<NAME> environment
+ * variables only seed the defaults and are read ONCE, at the first use of the library; afterwards an option changes
+ * only through this call.  Names (csrc/knobs.cuh): compact, compact_hetero, cw, l0_lists, occ, seg, seg_occ, l2_stream,
+ * l2_gather, sched_static, long_rows, occ16, l0_multi, l1_multi, l0_ws, dense_simt (1: exact fp32 FMA transforms
+ * instead of the 3xTF32 tensor-core products of the fp32 plan), prune_l0, fused, fused_sb.
+ * The reference has no counterpart (its arch call is a black box, model.py:104-112). */
+int xpgnn_set_option(const char* name, int32_t value);
+int xpgnn_get_option(const char* name, int32_t* value);
+
 /* ------------------------------------------------------------------------------------------
  * a1/a4  RNG stream + coalition masks
  * replaces: torch CPU generator draws inside Mask.mask_generator (masks.py:262-397),

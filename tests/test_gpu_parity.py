@@ -35,7 +35,7 @@ def _run_product(case, prune):
     if "rng_state" in case["z"].files:
         torch.set_rng_state(torch.from_numpy(case["z"]["rng_state"].copy()))
     ex = Explainer(feat, ei, arch, dict(meta["params"]), names, pathways, pnames, meta["element_type"], meta["problem"])
-    ex.options = dict(prune=prune)
+    ex.options = dict(prune=prune, keep_last=True)
     cfg, pdf = ex.run(meta["element"], meta["times"])
     return ex, cfg, pdf
 
@@ -239,7 +239,7 @@ def test_engine_matches_oracle_on_random_coalitions(kind, seed, lib):
 
 
 @pytest.mark.parametrize("hidden", [(32, 32), (64, 128, 64), (128, 128)])
-def test_fused_spmm_dense_matches_oracle(hidden, lib, monkeypatch):
+def test_fused_spmm_dense_matches_oracle(hidden, lib, knobs):
     """Layers >= 1 through the fused SpMM + tcgen05 (TF32x3) kernel, vs the oracle and vs the unfused path."""
     from bikg_graph_explainability_public_b200 import _lib
     from bikg_graph_explainability_public_b200.engine import GraphSpec, MaskedForward
@@ -254,16 +254,16 @@ def test_fused_spmm_dense_matches_oracle(hidden, lib, monkeypatch):
     act = torch.zeros((n, w), dtype=torch.int32, device="cuda")
     _lib.check(lib.xpgnn_pack_mask(m8.data_ptr(), s, n, act.data_ptr(), w, None, _lib.stream_ptr()))
     ys = {}
-    monkeypatch.setenv("XPGNN_COMPACT", "0")  # the compact path would take these shapes first
+    knobs(compact=0)  # the compact path would take these shapes first
     for fused in ("1", "0"):
-        monkeypatch.setenv("XPGNN_FUSED", fused)
+        knobs(fused=int(fused))
         eng = MaskedForward(GraphSpec(x.cuda(), ei.cuda(), [0, n]), lower(arch), [q])
         ys[fused] = eng(act, s)[:, 0].cpu().numpy()
         np.testing.assert_allclose(ys[fused], y_ref.numpy().reshape(-1), rtol=Y_RTOL, atol=Y_ATOL)
     np.testing.assert_allclose(ys["1"], ys["0"], rtol=2e-5, atol=1e-6)
     # 8-slot tiles in coalition-major order and a memory-limited 8-coalition tile give the same numbers
-    monkeypatch.setenv("XPGNN_FUSED", "1")
-    monkeypatch.setenv("XPGNN_FUSED_SB", "8")
+    knobs(fused=1)
+    knobs(fused_sb=8)
     eng = MaskedForward(GraphSpec(x.cuda(), ei.cuda(), [0, n]), lower(arch), [q], tile_coalitions=8)
     np.testing.assert_allclose(eng(act, s)[:, 0].cpu().numpy(), ys["1"], rtol=2e-5, atol=1e-6)
 
@@ -282,17 +282,17 @@ def _pack(lib, mask):
 @pytest.mark.gpu
 @pytest.mark.parametrize("kind,hidden,env", [
     ("gcn", (128, 128), {}),                          # row-outer layer 0 + list-driven layer 1 (the C3 shape)
-    ("gcn", (128, 128), {"XPGNN_L0": "lists"}),       # list-driven layer 0 with per-source weights
-    ("gcn", (128, 128), {"XPGNN_SCHED": "static"}),
+    ("gcn", (128, 128), {"l0_lists": 1}),       # list-driven layer 0 with per-source weights
+    ("gcn", (128, 128), {"sched_static": 1}),
     ("sage", (128, 128), {}),
-    ("sage", (128, 128), {"XPGNN_L0": "lists"}),
+    ("sage", (128, 128), {"l0_lists": 1}),
     ("gcn", (128,), {}),                              # single conv layer
     ("gcn", (16,), {}),                               # 16-wide chunks, SIMT transforms
     ("gcn", (32, 48), {}),
     ("sage", (64, 128, 64), {}),
     ("gcn", (192, 128), {}),                          # three 64-column blocks in the row-outer kernel
 ])
-def test_compact_path_matches_oracle(kind, hidden, env, lib, monkeypatch):
+def test_compact_path_matches_oracle(kind, hidden, env, lib, knobs):
     """Compact path (compact.cu: active rows only, per-coalition compacted edge lists, chunk-major
     activations) vs the oracle and vs the tile path of engine.cu, incl. coalitions in which the query
     node is inactive (isolated chain in the head), a partial last word and memory-limited tiles."""
@@ -307,7 +307,7 @@ def test_compact_path_matches_oracle(kind, hidden, env, lib, monkeypatch):
     assert (~mask[:, q]).sum() > 5 and mask[:, q].sum() > 5   # both the active and the isolated query branch
     act = _pack(lib, mask)
     for k, v in env.items():
-        monkeypatch.setenv(k, v)
+        knobs(**{k: v})
     g = GraphSpec(x.cuda(), ei.cuda(), [0, n])
     eng = MaskedForward(g, lower(arch), [q, (q + 1) % n, 5])
     y = eng(act, s).cpu().numpy()
@@ -319,13 +319,13 @@ def test_compact_path_matches_oracle(kind, hidden, env, lib, monkeypatch):
     eng8 = MaskedForward(g, lower(arch), [q, (q + 1) % n, 5], tile_coalitions=8)
     np.testing.assert_allclose(eng8(act, s).cpu().numpy(), y, rtol=1e-6, atol=1e-7)
     # the tile path of engine.cu computes every row; same predictions
-    monkeypatch.setenv("XPGNN_COMPACT", "0")
+    knobs(compact=0)
     legacy = MaskedForward(g, lower(arch), [q, (q + 1) % n, 5])
     np.testing.assert_allclose(legacy(act, s).cpu().numpy(), y, rtol=2e-5, atol=1e-6)
 
 
 @pytest.mark.parametrize("kind", ["gcn", "sage"])
-def test_compact_path_hub_rows(kind, lib, monkeypatch):
+def test_compact_path_hub_rows(kind, lib, knobs):
     """Destination rows above the long-row threshold (1024 in-edges) are processed by whole CTAs in the compact
     path (hub rows of power-law graphs); same predictions as the oracle and as the tile path."""
     from bikg_graph_explainability_public_b200.engine import GraphSpec, MaskedForward
@@ -355,10 +355,41 @@ def test_compact_path_hub_rows(kind, lib, monkeypatch):
     np.testing.assert_allclose(yp[:, 0], y[:, 0], rtol=2e-5, atol=1e-6)
     yp2 = MaskedForward(gs, lower(arch), [q], prune=True, hop=hop)(act, s).cpu().numpy()
     np.testing.assert_array_equal(yp2, yp)  # slices are added in a fixed order
-    monkeypatch.setenv("XPGNN_LONG", "0")   # hub rows through the row-per-warp kernels
+    knobs(long_rows=0)   # hub rows through the row-per-warp kernels
     np.testing.assert_allclose(MaskedForward(gs, lower(arch), [q, 7])(act, s).cpu().numpy(), y, rtol=2e-5, atol=1e-6)
-    monkeypatch.setenv("XPGNN_COMPACT", "0")
+    knobs(compact=0)
     np.testing.assert_allclose(MaskedForward(gs, lower(arch), [q, 7])(act, s).cpu().numpy(), y, rtol=2e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("kind", ["gcn", "sage"])
+@pytest.mark.parametrize("seg", ["0", "4", "6", "8"])
+def test_segmented_spmm_variants(kind, seg, lib, knobs):
+    """Layers >= 1 through the segmented SpMM (cspmm_seg_kernel: a warp sums the gather stream of a 32-row block in four
+    contiguous pieces) with 4 / 6 / 8 gathers in flight per lane, and through the row-lockstep kernel (0): medium hubs
+    (80-240 active in-edges, below the long-row threshold) make blocks longer than one staging round, rows cut by piece
+    and round boundaries, empty rows (SAGE) and a short last block; vs the oracle, bitwise repeatable."""
+    from bikg_graph_explainability_public_b200.engine import GraphSpec, MaskedForward
+    from bikg_graph_explainability_public_b200.lowering import lower
+    from oracle.xpgnn_oracle import kernel_output
+
+    x, ei, arch, mask, q = _random_model_case(21, kind, n=3001, e=9000, f=32, hidden=(128, 128, 64), s=45)
+    g = torch.Generator().manual_seed(77)
+    n = x.shape[0]
+    hubs = [q, 5, 6, 7, 8, 1500, 2999, 3000]
+    extra = [torch.stack([torch.randint(0, n, (k,), generator=g), torch.full((k,), h)])
+             for h, k in zip(hubs, (900, 400, 800, 333, 950, 700, 600, 850))]
+    ei = torch.cat([ei] + extra, 1)
+    s = mask.shape[0]
+    _, y_ref = kernel_output(mask.numpy(), x, ei.numpy(), arch, q)
+    act = _pack(lib, mask)
+    knobs(seg=int(seg))
+    gs = GraphSpec(x.cuda(), ei.cuda(), [0, n])
+    eng = MaskedForward(gs, lower(arch), [q, 5, 3000])
+    y = eng(act, s).cpu().numpy()
+    np.testing.assert_allclose(y[:, 0], y_ref.numpy().reshape(-1), rtol=Y_RTOL, atol=Y_ATOL)
+    _, y_ref5 = kernel_output(mask.numpy(), x, ei.numpy(), arch, 5)
+    np.testing.assert_allclose(y[:, 1], y_ref5.numpy().reshape(-1), rtol=Y_RTOL, atol=Y_ATOL)
+    np.testing.assert_array_equal(eng(act, s).cpu().numpy(), y)
 
 
 @pytest.mark.parametrize("kind", ["gcn", "sage"])
@@ -401,7 +432,7 @@ def test_compact_path_is_deterministic(lib):
 
 
 @pytest.mark.parametrize("seed", list(range(8)))
-def test_compact_path_randomized(seed, lib, monkeypatch):
+def test_compact_path_randomized(seed, lib, knobs):
     """Random configurations (conv kind, depth / widths, hubs, coalition count, tile size, query set): compact path vs
     the oracle and vs the tile path."""
     from bikg_graph_explainability_public_b200.engine import GraphSpec, MaskedForward
@@ -429,10 +460,10 @@ def test_compact_path_randomized(seed, lib, monkeypatch):
     tile = [None, 8, 4, 16][seed % 4]
     y = MaskedForward(gs, lower(arch), queries, tile_coalitions=tile)(act, s).cpu().numpy()
     np.testing.assert_allclose(y[:, 0], y_ref.numpy().reshape(-1), rtol=Y_RTOL, atol=Y_ATOL)
-    monkeypatch.setenv("XPGNN_COMPACT", "0")
+    knobs(compact=0)
     y_tile = MaskedForward(gs, lower(arch), queries)(act, s).cpu().numpy()
     np.testing.assert_allclose(y_tile, y, rtol=3e-5, atol=1e-6)
-    monkeypatch.delenv("XPGNN_COMPACT")
+    knobs(compact=1)
     if kind == "gcn" and all(h % 64 == 0 for h in hidden):  # bf16 activation storage where it applies
         y16 = MaskedForward(gs, lower(arch), queries, precision="bf16_act", tile_coalitions=tile)(act, s).cpu().numpy()
         np.testing.assert_allclose(y16, y, rtol=2e-2, atol=2e-3)
@@ -440,7 +471,7 @@ def test_compact_path_randomized(seed, lib, monkeypatch):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("kind", ["gcn", "sage"])
-def test_layer0_kernel_variants_agree(kind, lib, monkeypatch):
+def test_layer0_kernel_variants_agree(kind, lib, knobs):
     """The three layer-0 row kernels (XPGNN_L0_WS = 0 one warp per row, 1 warp specialised with column blocks, 2 warp
     specialised with slot x column tiles) do the same FMAs in the same order: outputs agree to rounding of the epilogue,
     on a graph with isolated rows, rows longer than one stage (> 16 / > 32 in-edges) and more than 16 active slots."""
@@ -458,7 +489,7 @@ def test_layer0_kernel_variants_agree(kind, lib, monkeypatch):
     g = GraphSpec(x.cuda(), ei.cuda(), [0, n])
     ys = []
     for mode in ("0", "1", "2"):
-        monkeypatch.setenv("XPGNN_L0_WS", mode)
+        knobs(l0_ws=int(mode))
         y = MaskedForward(g, lower(arch), [q, 3])(act, s).cpu().numpy()
         np.testing.assert_allclose(y[:, 0], y_ref, rtol=Y_RTOL, atol=Y_ATOL)
         ys.append(y)
@@ -467,7 +498,7 @@ def test_layer0_kernel_variants_agree(kind, lib, monkeypatch):
 
 
 @pytest.mark.parametrize("name", ["c4_tiny", "c2_wide", "c2_wide2"])
-def test_hetero_compact_path_matches_oracle(name, lib, monkeypatch):
+def test_hetero_compact_path_matches_oracle(name, lib, knobs):
     """Hetero compact path (per-relation compaction, relations into one destination type accumulate, merged root
     transform, isolated chain of typed queries, zero-edge rule) vs the oracle and vs the per-relation tile path."""
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -485,11 +516,11 @@ def test_hetero_compact_path_matches_oracle(name, lib, monkeypatch):
     y = eng(act, s)[:, 0].cpu().numpy()
     np.testing.assert_allclose(y, y_ref, rtol=Y_RTOL, atol=Y_ATOL)
     np.testing.assert_array_equal(eng(act, s, 32, 38)[:, 0].cpu().numpy(), y[32:70])
-    monkeypatch.setenv("XPGNN_L1_MULTI", "0")   # layers >= 1 aggregate-first relation by relation instead of transform-first per type
+    knobs(l1_multi=0)   # layers >= 1 aggregate-first relation by relation instead of transform-first per type
     np.testing.assert_allclose(eng(act, s)[:, 0].cpu().numpy(), y, rtol=3e-5, atol=1e-6)
-    monkeypatch.setenv("XPGNN_L0_MULTI", "0")   # layer 0 relation by relation (accumulate / finish) instead of one pass per type
+    knobs(l0_multi=0)   # layer 0 relation by relation (accumulate / finish) instead of one pass per type
     np.testing.assert_allclose(eng(act, s)[:, 0].cpu().numpy(), y, rtol=3e-5, atol=1e-6)
-    monkeypatch.setenv("XPGNN_COMPACT_HETERO", "0")
+    knobs(compact_hetero=0)
     _, eng_tile = wl.engine(torch.device("cuda", 0), "fp32")
     np.testing.assert_allclose(eng_tile(act, s)[:, 0].cpu().numpy(), y, rtol=3e-5, atol=1e-6)
 
