@@ -1,7 +1,8 @@
 """ORACLE / TEST INFRASTRUCTURE ONLY -- never imported by the product path.
 
 Imports the *unmodified* reference package from ``/root/reference/src`` in this
-container (it does not exist on the GPU box) behind four shims:
+container, or from its staged copy ``oracle/_ref/src`` on the GPU box (``oracle/stage_ref.py``: byte-for-byte, digests
+in ``oracle/_ref/MANIFEST.json``), behind four shims:
 
 1. ``torch_geometric`` -> ``oracle/pyg_standin`` (PyG 2.0.4 is not installed);
 2. ``inspect.getargspec`` (removed in Python 3.11; used at ``model.py:104``);
@@ -17,8 +18,11 @@ import inspect
 import os
 import sys
 
-REFERENCE_SRC = "/root/reference/src"
 _HERE = os.path.dirname(os.path.abspath(__file__))
+# the reference tree of the build container, else the byte-for-byte staged copy (oracle/stage_ref.py) that travels to the GPU box
+REFERENCE_SRC = "/root/reference/src"
+if not os.path.isdir(os.path.join(REFERENCE_SRC, "pathway_explanations")):
+    REFERENCE_SRC = os.path.join(_HERE, "_ref", "src")
 
 
 def reference_available():

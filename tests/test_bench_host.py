@@ -75,19 +75,46 @@ def test_rmat_generator_is_skewed_and_in_range():
 
 
 def test_reference_arm_prints_one_contract_line():
-    """`bench.py --impl reference` (the oracle port of the reference's CPU path) prints ONE JSON line with the
-    contract keys; it must work without a GPU."""
+    """`bench.py --impl reference` (the unmodified reference's kernel_output where the reference tree or its staged copy
+    exists, else the oracle port) prints ONE JSON line with the contract keys; it must work without a GPU."""
     import json
     import subprocess
 
     env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "tiny", "--steps", "1",
-                          "--warmup", "0", "--ref-coalitions", "2"], capture_output=True, text=True, env=env, timeout=600)
+                          "--warmup", "0", "--ref-coalitions", "2", "--no-query-leg"], capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "coalition evals/s" and d["unit"] == "coalition evals/s"
     assert d["value"] > 0 and d["higher_is_better"] is True and d["config"]["workload"] == "tiny"
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_and_port_agree_on_the_bench_workload():
+    """The two CPU arms of bench.py -- the unmodified reference's kernel_output and the oracle port -- give the same
+    predictions on a bench workload (skipped where neither /root/reference nor oracle/_ref exists)."""
+    ref = bench._reference_modules()
+    if ref is None:
+        pytest.skip("reference tree not present")
+    wl = bench.Workload("tiny")
+    om = wl.oracle_model(wl.make_model())
+    m = bench.make_masks(3, wl.n, wl.c, wl.com_of, 5).bool().numpy()
+    y_ref, kind = bench.host_eval(wl, om, m, ref)
+    y_port, kind2 = bench.host_eval(wl, om, m, None)
+    assert (kind, kind2) == ("reference", "port")
+    np.testing.assert_allclose(y_ref, y_port, rtol=1e-5, atol=1e-7)
+
+
+def test_strong_scaling_split_covers_the_job():
+    class A:
+        coalitions, coalitions_per_gpu = 4096, 0
+    for world in (1, 2, 3, 4, 8):
+        rows = bench.per_rank_rows(A, world)
+        assert sum(rows) == 4096 and all(r % 32 == 0 for r in rows[:-1]) and max(rows) - min(rows) <= 32
+    A.coalitions = 1000
+    assert sum(bench.per_rank_rows(A, 8)) == 1000
+    A.coalitions_per_gpu = 512
+    assert bench.per_rank_rows(A, 4) == [512] * 4 and bench.scaling_of(A) == "weak"
