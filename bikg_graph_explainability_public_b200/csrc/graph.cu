@@ -22,10 +22,24 @@ __global__ void khop_init_kernel(int8_t* hop, uint8_t* frontier, int64_t N, int6
 // one pass: next[src] = 1 for every edge whose dst is in cur.  PyG re-expands the whole previous
 // layer (visited nodes included), so `next` is not filtered by `hop`.
 __global__ void __launch_bounds__(256) khop_expand_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t E,
-                                                          const uint8_t* __restrict__ cur, uint8_t* __restrict__ next) {
+                                                          int64_t N, const uint8_t* __restrict__ cur, uint8_t* __restrict__ next) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < E; e += stride) {
+    const int64_t s = src[e], d = dst[e];
+    if ((uint64_t)s >= (uint64_t)N || (uint64_t)d >= (uint64_t)N) continue;  // counted by khop_validate_kernel
+    if (cur[d]) next[s] = 1;
+  }
+}
+
+// endpoints outside [0, N): PyG raises an index error; here they are counted (counts[2]) and the edge is ignored
+__global__ void __launch_bounds__(256) khop_validate_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t E,
+                                                            int64_t N, int64_t* __restrict__ n_bad) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int bad = 0;
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < E; e += stride)
-    if (cur[dst[e]]) next[src[e]] = 1;
+    bad += ((uint64_t)src[e] >= (uint64_t)N) || ((uint64_t)dst[e] >= (uint64_t)N);
+  bad = __reduce_add_sync(0xffffffffu, bad);
+  if ((threadIdx.x & 31) == 0 && bad) atomicAdd(reinterpret_cast<unsigned long long*>(n_bad), (unsigned long long)bad);
 }
 
 __global__ void khop_mark_kernel(int8_t* hop, const uint8_t* next, int64_t N, int level) {
@@ -51,11 +65,13 @@ __global__ void khop_relabel_kernel(const int8_t* hop, const int32_t* rank, int6
 }
 
 __global__ void __launch_bounds__(256) khop_edgeflag_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t E,
-                                                            const int8_t* __restrict__ hop, uint8_t* __restrict__ edge_mask,
+                                                            int64_t N, const int8_t* __restrict__ hop, uint8_t* __restrict__ edge_mask,
                                                             int32_t* __restrict__ flag) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < E; e += stride) {
-    const int k = (hop[src[e]] >= 0) && (hop[dst[e]] >= 0);
+    const int64_t s = src[e], d = dst[e];
+    const bool ok = (uint64_t)s < (uint64_t)N && (uint64_t)d < (uint64_t)N;
+    const int k = ok && (hop[s] >= 0) && (hop[d] >= 0);
     edge_mask[e] = (uint8_t)k;
     flag[e] = k;
   }
@@ -122,6 +138,7 @@ int xpgnn_khop_subgraph(const int64_t* edge_index, int64_t E, int64_t N, int64_t
                         void* stream) {
   XP_REQUIRE(N > 0 && query >= 0 && query < N, "query outside [0, N)");
   XP_REQUIRE(E >= 0 && hops >= 0 && hops < 127, "bad E / hops");
+  XP_REQUIRE(N < (1ll << 31) - 1 && E < (1ll << 31) - 1, "N/E out of int32 range (the scans and ranks are 32-bit)");
   XP_REQUIRE(subset && relabel && hop && counts && sub_edge_index && (edge_mask || E == 0), "null output");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t* src = edge_index;
@@ -136,10 +153,12 @@ int xpgnn_khop_subgraph(const int64_t* edge_index, int64_t E, int64_t N, int64_t
   uint8_t* nxt = cur + N;
   const int nb = (int)ceil_div(N, 256);
   const int eb = (int)std::min<int64_t>(std::max<int64_t>(ceil_div(E, 256), 1), kNumSMs * 16);
+  XP_CHECK(cudaMemsetAsync(counts + 2, 0, sizeof(int64_t), st));
+  if (E > 0) XP_LAUNCH(khop_validate_kernel, eb, 256, 0, st, src, dst, E, N, counts + 2);
   XP_LAUNCH(khop_init_kernel, nb, 256, 0, st, hop, cur, N, query);
   for (int h = 1; h <= hops; ++h) {
     XP_CHECK(cudaMemsetAsync(nxt, 0, N, st));
-    if (E > 0) XP_LAUNCH(khop_expand_kernel, eb, 256, 0, st, src, dst, E, cur, nxt);
+    if (E > 0) XP_LAUNCH(khop_expand_kernel, eb, 256, 0, st, src, dst, E, N, cur, nxt);
     XP_LAUNCH(khop_mark_kernel, nb, 256, 0, st, hop, nxt, N, h);
     std::swap(cur, nxt);
   }
@@ -152,7 +171,7 @@ int xpgnn_khop_subgraph(const int64_t* edge_index, int64_t E, int64_t N, int64_t
   XP_CHECK(cub::DeviceScan::ExclusiveSum(tmp.p, tb, nflag.as<int32_t>(), nrank.as<int32_t>(), (int)N, st));
   XP_LAUNCH(khop_relabel_kernel, nb, 256, 0, st, hop, nrank.as<int32_t>(), N, relabel, subset);
   if (E > 0) {
-    XP_LAUNCH(khop_edgeflag_kernel, eb, 256, 0, st, src, dst, E, hop, edge_mask, eflag.as<int32_t>());
+    XP_LAUNCH(khop_edgeflag_kernel, eb, 256, 0, st, src, dst, E, N, hop, edge_mask, eflag.as<int32_t>());
     XP_CHECK(cub::DeviceScan::ExclusiveSum(tmp.p, tb2, eflag.as<int32_t>(), erank.as<int32_t>(), (int)E, st));
     XP_LAUNCH(khop_edgewrite_kernel, eb, 256, 0, st, src, dst, E, eflag.as<int32_t>(), erank.as<int32_t>(), relabel,
               sub_edge_index);

@@ -30,11 +30,13 @@ def khop_subgraph(edge_index, n_nodes, query, hops):
     hop = torch.empty(n_nodes, dtype=torch.int8, device=dev)
     edge_mask = torch.zeros(max(e, 1), dtype=torch.uint8, device=dev)
     sub_ei = torch.empty((2, max(e, 1)), dtype=torch.int64, device=dev)
-    counts = torch.zeros(2, dtype=torch.int64, device=dev)
+    counts = torch.zeros(3, dtype=torch.int64, device=dev)
     _lib.check(lib.xpgnn_khop_subgraph(ei.data_ptr(), e, int(n_nodes), int(query), int(hops), subset.data_ptr(),
                                        relabel.data_ptr(), hop.data_ptr(), edge_mask.data_ptr(), sub_ei.data_ptr(),
                                        counts.data_ptr(), _lib.stream_ptr()))
-    n_sub, e_sub = (int(v) for v in counts.tolist())
+    n_sub, e_sub, n_bad = (int(v) for v in counts.tolist())
+    if n_bad:
+        raise IndexError("edge_index holds %d edge(s) with an endpoint outside [0, %d)" % (n_bad, n_nodes))
     subset = subset[:n_sub]
     sub_ei = sub_ei[:, :e_sub].contiguous()
     sub_ind = relabel[int(query)].to(torch.int64).reshape(1)

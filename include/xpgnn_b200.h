@@ -116,8 +116,9 @@ int xpgnn_pack_mask(const uint8_t* mask_rowmajor, int32_t S, int32_t N, uint32_t
  * worst case): subset int64 [N] ascending node ids; relabel int32 [N] (-1 outside);
  * hop int8 [N] first level a node was reached at (-1 outside); edge_mask uint8 [E];
  * sub_edge_index int64 [2][E] with row stride E (first counts[1] columns valid, original order,
- * relabelled); counts int64 [2] = {N_sub, E_sub}.  If no edge survives, one self loop on the
- * query is emitted (data.py:337-339) and counts[1] = 1. */
+ * relabelled); counts int64 [3] = {N_sub, E_sub, number of edges with an endpoint outside [0, N)}.  Such edges are
+ * ignored by the kernels and the caller raises (PyG raises an index error); N and E must fit int32.  If no edge
+ * survives, one self loop on the query is emitted (data.py:337-339) and counts[1] = 1. */
 int xpgnn_khop_subgraph(const int64_t* edge_index, int64_t E, int64_t N, int64_t query, int32_t hops,
                         int64_t* subset, int32_t* relabel, int8_t* hop, uint8_t* edge_mask,
                         int64_t* sub_edge_index, int64_t* counts, void* stream);

@@ -176,6 +176,17 @@ def test_khop_isolated_query_gets_self_loop():
     assert subset.tolist() == [0] and sub_ei.tolist() == [[0], [0]] and int(sub_ind) == 0
 
 
+def test_khop_rejects_out_of_range_edges():
+    """An endpoint outside [0, N) raises IndexError (PyG would too) instead of reading / writing out of bounds."""
+    from bikg_graph_explainability_public_b200.data import khop_subgraph
+
+    ei = torch.tensor([[0, 1, 7, 2], [1, 2, 3, -1]])
+    with pytest.raises(IndexError):
+        khop_subgraph(ei.cuda(), 5, 2, 2)
+    subset, sub_ei, *_ = khop_subgraph(ei[:, :2].cuda(), 5, 2, 2)
+    assert subset.cpu().tolist() == [0, 1, 2]
+
+
 def test_csr_is_stable_and_drops_self_loops():
     from bikg_graph_explainability_public_b200.engine import build_csr
 
