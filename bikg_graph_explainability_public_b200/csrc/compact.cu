@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(256) compact_finalize_kernel(const unsigned lo
 // first 128-row tile of every slot's active-row list, tile total, work counters, stats
 __global__ void __launch_bounds__(256) compact_tilemap_kernel(const int2* __restrict__ slot_info, int nb, int32_t* __restrict__ slot_tile_start,
                                                               int32_t* __restrict__ n_tiles, int n_layers,
-                                                              int64_t* stats, int32_t* __restrict__ counters) {
+                                                              int64_t* stats, int32_t* __restrict__ counters, int count_tile) {
   __shared__ int start[33];
   if (threadIdx.x < 16) counters[threadIdx.x] = 0;  // work counters of the SpMM launches of this tile
   if (threadIdx.x == 0) {
@@ -167,8 +167,8 @@ __global__ void __launch_bounds__(256) compact_tilemap_kernel(const int2* __rest
     start[nb] = acc;
     *n_tiles = acc;
     if (stats) {
-      stats[1] += active * n_layers;
-      stats[3] += 1;
+      stats[1] += active * n_layers;  // active edge visits of this CSR (one per conv layer that uses it)
+      stats[3] += count_tile;
     }
   }
   __syncthreads();
@@ -501,19 +501,33 @@ __global__ void __launch_bounds__(256) cspmm_long_kernel(const CspmmArgs a) {
 //   * the block's gather stream -- for GCN the row itself first (the operands of layers >= 1 are pre-scaled by
 //     deg^-1/2, so the unit self loop is one more unweighted term), then its active sources -- is staged in shared
 //     memory as words  id | row << 26 | last << 31 ;
-//   * the stream is cut into four equal contiguous pieces, one per group of 8 lanes (float4 each = one 128-byte row
-//     piece per group and gather), whatever the row lengths: a warp-level segmented sum.  Every lane keeps D gathers
-//     in flight through a rotating register queue; a word with the `last` bit closes its row: scale and store;
-//   * rows cut by a piece boundary are closed through shared memory in a fixed order (tail of the earlier piece, then
-//     the head of the later one), so the result does not depend on timing.
-// Rows with more than long_cnt active in-edges stay with cspmm_long_kernel.
+//   * the stream is cut at ROW boundaries into four pieces of about equal length, one per group of 8 lanes (float4
+//     each = one 128-byte row piece per group and gather): a warp-level segmented sum whose lanes stay busy whatever
+//     the row lengths.  Every lane keeps D gathers in flight through a rotating register queue; a word with the `last`
+//     bit closes its row: the sum goes to the warp's shared-memory tile (one predicated store, no divergent code);
+//   * the 32 sums are scaled and written by a converged epilogue, 4 rows per instruction.
+// Sums run in list order (self first), so results do not depend on the schedule.  Rows with more than long_cnt active
+// in-edges stay with cspmm_long_kernel.
 // ------------------------------------------------------------------------------------------
-constexpr int kSegCap = 256;  // stream positions staged per round (a 32-row block of C3 holds ~190)
-constexpr uint32_t kSegIdMask = (1u << kPackShift) - 1u;
+constexpr int kSegCap = 320;     // stream positions staged per round: >= kLongCompact + 1, so a row never straddles rounds
+constexpr int kSegTileLd = 36;   // floats per tile row (144 B: 16-byte aligned, consecutive rows 4 banks apart)
+constexpr int kSegRowwise = 24;  // blocks whose longest row has at most this many entries are staged row by row
+static_assert(kSegCap >= kLongCompact + 1 && kSegCap % 32 == 0, "a row (self + kLongCompact sources) must fit one round");
 
-__device__ __forceinline__ float4 seg_gather(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
-__device__ __forceinline__ void seg_store(float* p, const float4& acc, float sc) {
-  __stcs(reinterpret_cast<float4*>(p), make_float4(acc.x * sc, acc.y * sc, acc.z * sc, acc.w * sc));  // written once, read by the transform
+__device__ __forceinline__ float4 seg_gather(const char* base, uint32_t word) {  // word = source id | last << 31
+  const char* p;
+  asm("mad.wide.u32 %0, %1, 128, %2;" : "=l"(p) : "r"(word & 0x7fffffffu), "l"(base));  // one IMAD.WIDE: base + id * 128 bytes
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+__device__ __forceinline__ void seg_add(float4& acc, const float4& x) {
+  // two packed adds (FFMA2 with a unit multiplier) instead of four FADD: the loop is issue-bound before it is fabric-bound
+  asm("{\n\t.reg .b64 a0, a1, x0, x1, one;\n\t"
+      "mov.b64 a0, {%0, %1};\n\tmov.b64 a1, {%2, %3};\n\tmov.b64 x0, {%4, %5};\n\tmov.b64 x1, {%6, %7};\n\t"
+      "mov.b64 one, {0f3F800000, 0f3F800000};\n\t"
+      "fma.rn.f32x2 a0, x0, one, a0;\n\tfma.rn.f32x2 a1, x1, one, a1;\n\t"
+      "mov.b64 {%0, %1}, a0;\n\tmov.b64 {%2, %3}, a1;\n\t}"
+      : "+f"(acc.x), "+f"(acc.y), "+f"(acc.z), "+f"(acc.w)
+      : "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w));
 }
 
 template <int D, int OCC>
@@ -522,15 +536,12 @@ __global__ void __launch_bounds__(128, OCC) cspmm_seg_kernel(const CspmmArgs a) 
   __shared__ int s_start[33];
   __shared__ int s_nact[32];
   __shared__ __align__(16) uint32_t s_ids[WARPS][kSegCap];
-  __shared__ int s_rowv[WARPS][32];
-  __shared__ float s_rowscale[WARPS][32];
+  __shared__ __align__(16) float s_tile[WARPS][32 * kSegTileLd];
+  __shared__ int s_rowv[WARPS][32];        // original node id | -1: no row / hub row (not written here)
   __shared__ int s_aend[WARPS][32];        // stream position one past the row's last entry
   __shared__ uint32_t s_e[WARPS][32];      // first list entry of the row
-  __shared__ __align__(16) float s_head[WARPS][4][32];
-  __shared__ __align__(16) float s_tail[WARPS][4][32];
-  __shared__ __align__(16) float s_cr[WARPS][32];
-  __shared__ int s_headrow[WARPS][4];
-  __shared__ int s_next[WARPS][4];         // decoded item n + 1 (slot, chunk, first row)
+  __shared__ uint32_t s_cnt[WARPS][32];    // active in-edges of the row
+  __shared__ int s_next[WARPS][2];         // decoded item n + 1 (slot, chunk)
   if (threadIdx.x <= a.nb) s_start[threadIdx.x] = a.slot_tile_start[threadIdx.x];
   if (threadIdx.x < a.nb) s_nact[threadIdx.x] = a.slot_info[threadIdx.x].x;
   __syncthreads();
@@ -538,6 +549,7 @@ __global__ void __launch_bounds__(128, OCC) cspmm_seg_kernel(const CspmmArgs a) 
   const int total = s_start[a.nb] * a.n_chunks * 4;  // items = 32-row blocks, ordered slot / chunk / 128-row tile / quarter
   const bool gcn = a.kind == XPGNN_CONV_GCN;
   uint32_t* ids = s_ids[warp];
+  float* tile = s_tile[warp];
 
   // ---- two-deep item pipeline: item n is processed while the metadata loads of n + 1 and the counter fetch of n + 2 fly ----
   int t_cur = 0;
@@ -575,121 +587,141 @@ __global__ void __launch_bounds__(128, OCC) cspmm_seg_kernel(const CspmmArgs a) 
     __syncwarp();
     const int t = s_next[warp][0], c = s_next[warp][1];
     __syncwarp();
+    int nA, n_l, v_l;
+    uint32_t e_l, nonempty;
     {
-      const int v_l = v1;
-      const uint32_t e_l = e1, cnt_l = f1 - e1;
-      item1 = item2;
-      load_meta(item1, v1, e1, f1);   // consumed at the top of the next iteration
-      item2 = grab();
-      const bool valid = v_l >= 0;
+      const uint32_t cnt_l = f1 - e1;
       const bool is_long = a.long_cnt > 0 && cnt_l > (uint32_t)a.long_cnt;
-      const int n_l = (valid && !is_long) ? (int)cnt_l + (gcn ? 1 : 0) : 0;
-      // inclusive prefix of the stream lengths
-      int a_end = n_l;
+      const bool mine = v1 >= 0 && !is_long;
+      n_l = mine ? (int)cnt_l + (gcn ? 1 : 0) : 0;
+      v_l = v1; e_l = e1;
+      int a_end = n_l;  // inclusive prefix of the stream lengths
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const int y = __shfl_up_sync(0xffffffffu, a_end, o);
         if (lane >= o) a_end += y;
       }
-      s_rowv[warp][lane] = v_l;
-      s_rowscale[warp][lane] = gcn ? gcn_dinv(cnt_l) : 1.0f / (float)max(cnt_l, 1u);
+      s_rowv[warp][lane] = mine ? v1 : -1;
       s_aend[warp][lane] = a_end;
-      s_e[warp][lane] = e_l;
-      s_cr[warp][lane] = 0.0f;
-      // SAGE: a row without an active in-edge aggregates to zero and has no stream entry
-      uint32_t empties = __ballot_sync(0xffffffffu, valid && !is_long && n_l == 0);
-      while (empties) {
-        const int r = __ffs(empties) - 1;
-        empties &= empties - 1;
-        const int vr = __shfl_sync(0xffffffffu, v_l, r);
-        if (lane < 8)
-          __stcs(reinterpret_cast<float4*>(a.out + (int64_t)t * a.out_s_stride + (int64_t)c * a.out_chunk_stride + (int64_t)vr * 32 + lane * 4),
-                 make_float4(0.f, 0.f, 0.f, 0.f));
-      }
+      s_e[warp][lane] = e1;
+      s_cnt[warp][lane] = cnt_l;
+      nA = __shfl_sync(0xffffffffu, a_end, 31);
+      nonempty = __ballot_sync(0xffffffffu, n_l > 0);  // the tile holds the sums of these rows, in row order
+      item1 = item2;
+      load_meta(item1, v1, e1, f1);   // consumed at the top of the next iteration
+      item2 = grab();
     }
+    const int n_max = __reduce_max_sync(0xffffffffu, n_l);
     __syncwarp();
-    const int nA = s_aend[warp][31];
     const int32_t* cc = a.ccol + a.slot_base[t];
-    const float* in_c = a.in + (int64_t)t * a.in_s_stride + (int64_t)c * a.in_chunk_stride + sub * 4;
-    float* out_c = a.out + (int64_t)t * a.out_s_stride + (int64_t)c * a.out_chunk_stride + sub * 4;
+    const char* in_c = reinterpret_cast<const char*>(a.in + (int64_t)t * a.in_s_stride + (int64_t)c * a.in_chunk_stride + sub * 4);
 
-    for (int S = 0; S < nA; S += kSegCap) {
-      const int len = min(kSegCap, nA - S);
-      // ---- stage the stream words of this round ----
-      for (int i = lane; i < len; i += 32) {
-        const int pos = S + i;
-        int r = 0;  // rows whose stream ends at or before pos
+    int r_lo = 0;  // rows [r_lo, r_hi) of this round: as many whole rows as fit kSegCap positions
+    while (r_lo < 32) {
+      const int base = r_lo ? s_aend[warp][r_lo - 1] : 0;
+      if (base >= nA) break;  // the remaining rows have no entries
+      const uint32_t over = __ballot_sync(0xffffffffu, s_aend[warp][lane] - base > kSegCap) & ~((1u << r_lo) - 1u);
+      const int r_hi = over ? __ffs(over) - 1 : 32;
+      const int len = s_aend[warp][r_hi - 1] - base;
+      const int a_l = (lane ? s_aend[warp][lane - 1] : 0) - base;  // start of row `lane` relative to the round
+      const bool in_round = lane >= r_lo && lane < r_hi;
+      // ---- stage the stream words of this round: source id | last << 31 ----
+      if (n_max <= kSegRowwise) {  // short rows: lane = row
+        if (in_round && n_l > 0) {
+          int o = a_l;
+          if (gcn) ids[o++] = (uint32_t)v_l | (n_l == 1 ? 0x80000000u : 0u);
+          const int ne = n_l - (gcn ? 1 : 0);
+          for (int k = 0; k < ne; ++k) ids[o + k] = (uint32_t)__ldg(cc + e_l + k) | (k == ne - 1 ? 0x80000000u : 0u);
+        }
+      } else {                     // lane = stream position, its row by binary search over the row ends
+        for (int i = lane; i < len; i += 32) {
+          const int pos = base + i;
+          int r = 0;  // rows whose stream ends at or before pos
 #pragma unroll
-        for (int step = 16; step >= 1; step >>= 1)
-          if (s_aend[warp][r + step - 1] <= pos) r += step;
-        const int ar = r ? s_aend[warp][r - 1] : 0;
-        int id;
-        if (gcn) id = pos == ar ? s_rowv[warp][r] : __ldcs(cc + s_e[warp][r] + (uint32_t)(pos - ar - 1));
-        else id = __ldcs(cc + s_e[warp][r] + (uint32_t)(pos - ar));
-        ids[i] = (uint32_t)id | ((uint32_t)r << kPackShift) | (pos == s_aend[warp][r] - 1 ? 0x80000000u : 0u);
+          for (int step = 16; step >= 1; step >>= 1)
+            if (s_aend[warp][r + step - 1] <= pos) r += step;
+          const int ar = r ? s_aend[warp][r - 1] : 0;
+          int id;
+          if (gcn) id = pos == ar ? s_rowv[warp][r] : __ldcs(cc + s_e[warp][r] + (uint32_t)(pos - ar - 1));
+          else id = __ldcs(cc + s_e[warp][r] + (uint32_t)(pos - ar));
+          ids[i] = (uint32_t)id | (pos == s_aend[warp][r] - 1 ? 0x80000000u : 0u);
+        }
       }
-      __syncwarp();
-      // ---- stream: four contiguous pieces, D gathers in flight per lane ----
+      // ---- cut at row boundaries into four pieces of ~len / 4 positions: piece g starts at the first non-empty row that
+      // begins at or after position g * per; its sums go to consecutive tile rows ----
       const int per = (len + 3) >> 2;
-      const int q1 = min((grp + 1) * per, len);
-      int q = min(grp * per, len);
+      int q = 0, q1 = len, trow = __popc(nonempty & ((1u << r_lo) - 1u));
+#pragma unroll
+      for (int g = 1; g < 4; ++g) {
+        const uint32_t m = __ballot_sync(0xffffffffu, in_round && n_l > 0 && a_l >= g * per);
+        const int first = m ? __ffs(m) - 1 : 32;
+        const int start = m ? __shfl_sync(0xffffffffu, a_l, first & 31) : len;
+        if (grp == g) { q = start; trow = __popc(nonempty & ((1u << (first & 31)) - 1u)); }
+        if (grp == g - 1) q1 = start;
+      }
+      uint32_t tp = (uint32_t)__cvta_generic_to_shared(tile + trow * kSegTileLd + sub * 4);
+      __syncwarp();
+      // ---- stream: D gathers in flight per lane; a `last` word closes its row into the tile ----
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      int headrow = -1;
       float4 x[D];
       uint32_t w[D];
+      auto close_row = [&](uint32_t wk) {
+        if ((int)wk < 0) {
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(tp), "f"(acc.x), "f"(acc.y), "f"(acc.z), "f"(acc.w) : "memory");
+          tp += kSegTileLd * 4;
+          acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
 #pragma unroll
       for (int k = 0; k < D; ++k) {
         w[k] = 0; x[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (q + k < q1) {
           w[k] = ids[q + k];
-          x[k] = seg_gather(in_c + (int64_t)(w[k] & kSegIdMask) * 32);
+          x[k] = seg_gather(in_c, w[k]);
         }
       }
-      for (; q < q1; q += D) {
+      for (; q + 2 * D <= q1; q += D) {  // steady state: every queue slot is consumed and refilled, no predicates
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          const uint32_t wk = w[k];
+          seg_add(acc, x[k]);
+          w[k] = ids[q + k + D];
+          x[k] = seg_gather(in_c, w[k]);
+          close_row(wk);
+        }
+      }
+      for (; q < q1; q += D) {           // drain
 #pragma unroll
         for (int k = 0; k < D; ++k) {
           if (q + k < q1) {
             const uint32_t wk = w[k];
-            acc.x += x[k].x; acc.y += x[k].y; acc.z += x[k].z; acc.w += x[k].w;
+            seg_add(acc, x[k]);
             if (q + k + D < q1) {
               w[k] = ids[q + k + D];
-              x[k] = seg_gather(in_c + (int64_t)(w[k] & kSegIdMask) * 32);
+              x[k] = seg_gather(in_c, w[k]);
             }
-            if (wk >> 31) {  // the row ends here
-              const int r = (wk >> kPackShift) & 31;
-              if (headrow < 0) {  // first row closed by this piece: it may have started in an earlier piece
-                headrow = r;
-                *reinterpret_cast<float4*>(&s_head[warp][grp][sub * 4]) = acc;
-              } else {
-                seg_store(out_c + (int64_t)s_rowv[warp][r] * 32, acc, s_rowscale[warp][r]);
-              }
-              acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+            close_row(wk);
           }
         }
       }
-      // ---- close the rows cut by piece / round boundaries, in piece order ----
-      *reinterpret_cast<float4*>(&s_tail[warp][grp][sub * 4]) = acc;
-      if (sub == 0) s_headrow[warp][grp] = headrow;
       __syncwarp();
-      float4 cy = *reinterpret_cast<const float4*>(&s_cr[warp][sub * 4]);  // open row carried in from the previous round
-      for (int h = 0; h < grp; ++h) {
-        const float4 tl = *reinterpret_cast<const float4*>(&s_tail[warp][h][sub * 4]);
-        if (s_headrow[warp][h] >= 0) cy = tl;
-        else { cy.x += tl.x; cy.y += tl.y; cy.z += tl.z; cy.w += tl.w; }
+      r_lo = r_hi;
+    }
+    // ---- epilogue: scale and write the 32 rows, 4 rows per instruction ----
+    float* out_c = a.out + (int64_t)t * a.out_s_stride + (int64_t)c * a.out_chunk_stride + sub * 4;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int r = it * 4 + grp;
+      const int v = s_rowv[warp][r];
+      if (v >= 0) {
+        const uint32_t cnt = s_cnt[warp][r];
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);  // SAGE row without an active in-edge: empty mean
+        float sc = 0.f;
+        if (gcn) sc = gcn_dinv(cnt);
+        else if (cnt) sc = 1.0f / (float)cnt;
+        if (gcn || cnt) o = *reinterpret_cast<const float4*>(tile + __popc(nonempty & ((1u << r) - 1u)) * kSegTileLd + sub * 4);
+        __stcs(reinterpret_cast<float4*>(out_c + (int64_t)v * 32), make_float4(o.x * sc, o.y * sc, o.z * sc, o.w * sc));
       }
-      if (headrow >= 0) {
-        const float4 hd = *reinterpret_cast<const float4*>(&s_head[warp][grp][sub * 4]);
-        seg_store(out_c + (int64_t)s_rowv[warp][headrow] * 32, make_float4(cy.x + hd.x, cy.y + hd.y, cy.z + hd.z, cy.w + hd.w),
-                  s_rowscale[warp][headrow]);
-      }
-      __syncwarp();
-      if (grp == 3) {  // what stays open after the last piece goes to the next round
-        float4 co = acc;
-        if (headrow < 0) { co.x += cy.x; co.y += cy.y; co.z += cy.z; co.w += cy.w; }
-        *reinterpret_cast<float4*>(&s_cr[warp][sub * 4]) = co;
-      }
-      __syncwarp();
     }
   }
 }
@@ -1186,7 +1218,7 @@ int forward_compact(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32
         XP_LAUNCH(compact_finalize_kernel, dim3((unsigned)ceil_div(N, 256), (unsigned)nb), 256, 0, st, lay.keys, lay.scanned, N, 0,
                   lay.act_list, lay.rowptr_c, (kind == XPGNN_CONV_GCN && !l0_rows) ? lay.wgt : nullptr, lay.slot_info, lay.slot_base,
                   lay.rows_packed, lay.rs_packed, n_long > 0 ? kLongCompact : 0, lay.long_list, lay.n_long_list);
-        XP_LAUNCH(compact_tilemap_kernel, 1, 256, 0, st, lay.slot_info, nb, lay.slot_tile_start, lay.n_tiles, NL, stats, lay.counters);
+        XP_LAUNCH(compact_tilemap_kernel, 1, 256, 0, st, lay.slot_info, nb, lay.slot_tile_start, lay.n_tiles, NL, stats, lay.counters, 1);
         XP_LAUNCH(compact_edges_kernel, grid_rows, 256, 0, st, R0.rowptr, R0.col, lay.ebits, act, W, w, b0, nb, N, lay.scanned, lay.ccol,
                   lay.counters + 14, n_long > 0 ? kLongRow : 0, 0);
         if (n_long > 0)
@@ -1382,6 +1414,7 @@ __global__ void compact_sum_active_kernel(const int2* __restrict__ slot_info, in
 struct HCsr {  // one unique relation CSR and its per-tile compaction
   const int32_t *rowptr, *col;
   int kind, lo, hi, n_edges, n_long;
+  int n_layers_using;  // conv layers whose relations map to this CSR (active-edge statistics)
   uint32_t* ebits;
   float *scale, *wgt, *rs_packed;
   int32_t *act_list, *slot_tile_start, *n_tiles, *counters, *long_rows, *n_long_dev, *long_list, *n_long_list, *rows_packed, *ccol;
@@ -1451,6 +1484,7 @@ static HLayout hetero_carve(const xpgnn_plan_t* p, void* ws, int64_t cap, int ti
         id = (int)h.csr.size() - 1;
       }
       h.map[l][r] = id;
+      h.csr[id].n_layers_using += 1;
     }
   }
   const xpgnn_layer_t& L0 = p->layers_host[0];
@@ -1660,8 +1694,8 @@ int forward_compact_hetero(const xpgnn_plan_t* p, const uint32_t* act, int32_t W
         XP_LAUNCH(compact_finalize_kernel, dim3((unsigned)ceil_div(nd, 256), (unsigned)nb), 256, 0, st, lay.keys, lay.scanned, nd, c.lo,
                   c.act_list, c.rowptr_c, c.wgt, c.slot_info, c.slot_base, c.rows_packed, c.rs_packed, lt ? kLongCompact : 0,
                   c.long_list, c.n_long_list);
-        XP_LAUNCH(compact_tilemap_kernel, 1, 256, 0, st, c.slot_info, nb, c.slot_tile_start, c.n_tiles, NL, i == 0 ? stats : nullptr,
-                  c.counters);
+        XP_LAUNCH(compact_tilemap_kernel, 1, 256, 0, st, c.slot_info, nb, c.slot_tile_start, c.n_tiles, c.n_layers_using, stats,
+                  c.counters, i == 0 ? 1 : 0);
         XP_LAUNCH(compact_edges_kernel, grid_nd, 256, 0, st, c.rowptr, c.col, c.ebits, act, W, w, b0, nb, nd, lay.scanned, c.ccol,
                   c.counters + 14, lt, c.lo);
         if (c.n_long > 0)

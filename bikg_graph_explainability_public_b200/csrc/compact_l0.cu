@@ -311,6 +311,15 @@ __device__ __forceinline__ void ws_mbar_wait_timed(uint64_t* bar, uint32_t parit
   }
 }
 constexpr int kWsProducerSleep = 256, kWsConsumerSleep = 32;  // ns between polls: the producers run ahead, the consumers are the critical path
+__device__ __forceinline__ void ws_mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ws_u32(bar)), "r"(bytes) : "memory");
+}
+// one bulk copy (TMA unit) global -> shared, size a multiple of 16 bytes, both ends 16-byte aligned
+__device__ __forceinline__ void ws_bulk_copy(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(ws_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(ws_u32(bar))
+               : "memory");
+}
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {  // through L1: neighbouring 16-byte pieces share a sector
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(ws_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
@@ -390,7 +399,10 @@ __device__ __forceinline__ void l0_epilogue_tab(const L0RowsArgs& a, const WsW& 
   }
 }
 
-template <bool SIGMOID, bool OUT16, bool PLAIN, bool DBG>
+// BULK: every producer lane moves its in-edge's 256-byte Z piece with ONE bulk copy (cp.async.bulk = the TMA unit, SASS
+// UBLKCP; completion counted in bytes on the stage's mbarrier) instead of 16 lanes x 16-byte cp.async per in-edge: the
+// pieces no longer pass through the LSU / shared-memory store pipe the consumers' LDS traffic saturates.
+template <bool SIGMOID, bool OUT16, bool PLAIN, bool DBG, bool BULK>
 __global__ void __launch_bounds__(2 * kWsPairs * 32, 1) l0_ws_kernel(const L0RowsArgs a) {
   extern __shared__ __align__(128) uint8_t ws_smem[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -398,10 +410,12 @@ __global__ void __launch_bounds__(2 * kWsPairs * 32, 1) l0_ws_kernel(const L0Row
   WsPair& P = reinterpret_cast<WsPair*>(ws_smem)[producer ? wid : wid - kWsPairs];
   if (producer && lane == 0) {
     for (int i = 0; i < 2; ++i) {
-      ws_mbar_init(&P.zfull[i], 33);  // 32 cp.async completions (one per producer lane) + the header / weights arrival
+      // 32 cp.async completions (one per producer lane) + the header / weights arrival | BULK: that arrival + the bytes
+      ws_mbar_init(&P.zfull[i], BULK ? 1 : 33);
       ws_mbar_init(&P.zempty[i], 1);
       ws_mbar_init(&P.wempty[i], 1);
     }
+    if (BULK) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   const uint32_t live = (a.nb == 32 ? 0xffffffffu : ((1u << a.nb) - 1u)) << a.b0;  // bits of the word in this tile
@@ -516,8 +530,9 @@ __global__ void __launch_bounds__(2 * kWsPairs * 32, 1) l0_ws_kernel(const L0Row
           }
           const int stage = zs & 1;
           ws_mbar_wait_timed<kWsProducerSleep>(&P.zempty[stage], ((zs >> 1) & 1) ^ 1, timed, t_wait1);
-          // Z pieces: 16 lanes x 16 bytes per in-edge, two in-edges per instruction (coalesced 256-byte requests)
-          {
+          if (BULK) {  // Z pieces: one 256-byte bulk copy per in-edge, issued by the lane that owns the edge
+            if (lane < n) ws_bulk_copy(&P.z[stage][lane][0], a.z + (int64_t)u * a.h0 + cb * 64, 256, &P.zfull[stage]);
+          } else {     // 16 lanes x 16 bytes per in-edge, two in-edges per instruction (coalesced 256-byte requests)
             const int uo = u * a.h0;  // element offset of the lane's own source row (N * h0 < 2^31: checked on the host)
             const float* zc = a.z + cb * 64 + (lane & 15) * 4;
             float* zd = &P.z[stage][lane >> 4][(lane & 15) * 4];
@@ -527,7 +542,7 @@ __global__ void __launch_bounds__(2 * kWsPairs * 32, 1) l0_ws_kernel(const L0Row
               if (jj + (lane >> 4) < n) cp_async16_cg(zd + jj * 64, zc + o);
             }
           }
-          ws_cp_async_arrive(&P.zfull[stage]);
+          if (!BULK) ws_cp_async_arrive(&P.zfull[stage]);
           const bool last_batch = base + 32 >= e1;
           if (lane == 0) {
             WsHdr h;
@@ -537,7 +552,10 @@ __global__ void __launch_bounds__(2 * kWsPairs * 32, 1) l0_ws_kernel(const L0Row
             P.hdr[stage] = h;
           }
           __syncwarp();
-          if (lane == 0) ws_mbar_arrive(&P.zfull[stage]);  // releases the header, the tables and the weight rows of all lanes
+          if (lane == 0) {  // releases the header, the tables and the weight rows of all lanes
+            if (BULK) ws_mbar_arrive_expect_tx(&P.zfull[stage], (uint32_t)n * 256u);
+            else ws_mbar_arrive(&P.zfull[stage]);
+          }
           ++zs;
           base += 32;
           // the row's remaining weight buffers come before the next row's: only prefetch into a buffer once this row
@@ -550,7 +568,7 @@ __global__ void __launch_bounds__(2 * kWsPairs * 32, 1) l0_ws_kernel(const L0Row
     const int stage = zs & 1;  // end marker
     ws_mbar_wait<kWsProducerSleep>(&P.zempty[stage], ((zs >> 1) & 1) ^ 1);
     if (lane == 0) P.hdr[stage].flags = WS_END;
-    ws_cp_async_arrive(&P.zfull[stage]);
+    if (!BULK) ws_cp_async_arrive(&P.zfull[stage]);
     __syncwarp();
     if (lane == 0) ws_mbar_arrive(&P.zfull[stage]);
     if (timed && lane == 0) {
@@ -1023,7 +1041,8 @@ __global__ void __launch_bounds__(256, 2) l0_multi_kernel(const L0MultiArgs a) {
 // layer-0 row kernel over the rows that are not hub rows: warp specialised by default, XPGNN_L0_WS=0 selects the
 // one-warp-per-row kernel (same arithmetic, same order: bit-identical)
 int launch_l0_rows(const L0RowsArgs& r, bool sigmoid, bool out16, int n_rows, cudaStream_t st) {
-  // XPGNN_L0_WS: 1 (default) warp specialised, column-block tiling; 2 warp specialised, slot x column tiling (widths % 128 == 0:
+  // l0_ws option: 3 = 1 with the Z pieces moved by TMA bulk copies (UBLKCP) instead of cp.async;
+  // 1 (default) warp specialised, column-block tiling; 2 warp specialised, slot x column tiling (widths % 128 == 0:
   // 40 % fewer shared-memory wavefronts and fewer cycles, but a lower clock under the power cap -- 6.2 against 5.3 ms at C3);
   // 0 one warp per row.  Read per call so that the tests can compare the three.
   const int ws_env = knobs().l0_ws;
@@ -1044,10 +1063,13 @@ int launch_l0_rows(const L0RowsArgs& r, bool sigmoid, bool out16, int n_rows, cu
         : plain ? (sigmoid ? l0_ws2_kernel<true, false, true, false> : l0_ws2_kernel<false, false, true, false>)
                 : (sigmoid ? l0_ws2_kernel<true, false, false, false> : l0_ws2_kernel<false, false, false, false>);
     else
-      k = dbg    ? l0_ws_kernel<false, false, true, true>
-        : out16  ? (sigmoid ? l0_ws_kernel<true, true, true, false> : l0_ws_kernel<false, true, true, false>)
-        : plain ? (sigmoid ? l0_ws_kernel<true, false, true, false> : l0_ws_kernel<false, false, true, false>)
-                : (sigmoid ? l0_ws_kernel<true, false, false, false> : l0_ws_kernel<false, false, false, false>);
+      k = dbg    ? l0_ws_kernel<false, false, true, true, false>
+        : ws == 3 ? (out16  ? (sigmoid ? l0_ws_kernel<true, true, true, false, true> : l0_ws_kernel<false, true, true, false, true>)
+                    : plain ? (sigmoid ? l0_ws_kernel<true, false, true, false, true> : l0_ws_kernel<false, false, true, false, true>)
+                            : (sigmoid ? l0_ws_kernel<true, false, false, false, true> : l0_ws_kernel<false, false, false, false, true>))
+        : out16  ? (sigmoid ? l0_ws_kernel<true, true, true, false, false> : l0_ws_kernel<false, true, true, false, false>)
+        : plain ? (sigmoid ? l0_ws_kernel<true, false, true, false, false> : l0_ws_kernel<false, false, true, false, false>)
+                : (sigmoid ? l0_ws_kernel<true, false, false, false, false> : l0_ws_kernel<false, false, false, false, false>);
     const int smem = ws == 2 ? kW2SmemBytes : kWsSmemBytes;
     XP_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     L0RowsArgs rr = r;

@@ -317,19 +317,16 @@ class Explainer:
         hop = data_class.last_hop
         query_flat = int(sub_ind[0])
 
-        sub_pathway = sub_pathway_names = None
+        sub_pathway_inds = sub_pathway_names = None
         if self.pathways is not None:
-            sub_pathway, sub_pathway_names, _ = pathway_class.comp_graph(sub_names)
+            # pathways.py:33-136 (comp_graph + names2inds) in one vectorised pass; see Pathways.resolve_indices
+            sub_pathway_inds, sub_pathway_names = pathway_class.resolve_indices(sub_names)
+            if not sub_pathway_inds:
+                raise IndexError("list index out of range")  # explainer.py:467: no community reaches the computational graph
+            sub_pathway_class = Pathways(sub_pathway_inds, sub_pathway_names)
         if self.element_type is not None or self.node_types is not None or self.edge_types is not None:
             filtered = self.filter_hetero_names(sub_names, sub_nt, sub_et, ntn, etn)
             sub_ind = torch.tensor([self.extract_index(element, filtered)])
-        sub_pathway_inds = None
-        if self.pathways is not None:
-            sub_pathway_class = Pathways(sub_pathway, sub_pathway_names)
-            if isinstance(sub_pathway[0][0], str):
-                sub_pathway_inds = sub_pathway_class.names2inds(sub_names, index=pathway_class.last_index, filtered=True)
-            elif isinstance(sub_pathway[0][0], int):
-                sub_pathway_inds = sub_pathway
         del self.feat, self.edge_index  # explainer.py:476: the object is single use
 
         elements = int(sub_feat.shape[0])

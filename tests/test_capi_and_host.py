@@ -217,3 +217,28 @@ def test_name_resolution_fast_path_equals_intersect1d(case):
     pw = Pathways(communities, cnames)
     sub2, sub_cnames2, _ = pw.comp_graph(sub_names)
     assert Pathways(sub2, sub_cnames2).names2inds(sub_names, index=pw.last_index, filtered=True) == ref_inds
+
+
+def test_resolve_indices_equals_comp_graph_then_names2inds():
+    """``Pathways.resolve_indices`` (the vectorised pass ``Explainer.run`` uses) returns, per community, the same index
+    set as ``comp_graph`` followed by ``names2inds`` (the reference's two intersect1d passes, pathways.py:84-96,131-134),
+    in ascending order -- the order ``Mask.mask_generator`` sorts them into anyway (masks.py:323) -- incl. duplicate
+    names (first occurrence wins), duplicate members, communities that miss the subgraph and integer members."""
+    import random
+
+    from bikg_graph_explainability_public_b200.pathways import Pathways
+
+    rnd = random.Random(3)
+    names = ["n%d" % rnd.randrange(300) for _ in range(400)]
+    coms = [["n%d" % rnd.randrange(500) for _ in range(rnd.randrange(1, 40))] for _ in range(30)] + [["zz1", "zz2"]]
+    cn = ["c%d" % i for i in range(len(coms))]
+    sub, sn, _ = Pathways([list(c) for c in coms], cn).comp_graph(names)
+    want = [sorted(x) for x in Pathways(sub, sn).names2inds(names)]
+    got, got_names = Pathways([list(c) for c in coms], cn).resolve_indices(names)
+    assert got_names == sn and got == want and "c30" not in got_names
+    coms_i = [[rnd.randrange(500) for _ in range(20)] for _ in range(10)]
+    names_i = [str(i) for i in range(250)]
+    sub, sn, _ = Pathways([list(c) for c in coms_i], None).comp_graph(names_i)
+    want = [sorted(x) for x in Pathways(sub, sn).names2inds(names_i)]
+    got, got_names = Pathways([list(c) for c in coms_i], None).resolve_indices(names_i)
+    assert got_names == sn and got == want

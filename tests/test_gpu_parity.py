@@ -17,6 +17,7 @@ import golden_io as gio
 
 pytestmark = pytest.mark.gpu
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 Y_RTOL, Y_ATOL = 1e-4, 1e-6      # perturbed predictions (fp32 path)
 W_TOL = 1e-3                      # importances / community scores
 
@@ -483,8 +484,8 @@ def test_compact_path_randomized(seed, lib, knobs):
 @pytest.mark.gpu
 @pytest.mark.parametrize("kind", ["gcn", "sage"])
 def test_layer0_kernel_variants_agree(kind, lib, knobs):
-    """The three layer-0 row kernels (XPGNN_L0_WS = 0 one warp per row, 1 warp specialised with column blocks, 2 warp
-    specialised with slot x column tiles) do the same FMAs in the same order: outputs agree to rounding of the epilogue,
+    """The layer-0 row kernels (option l0_ws = 0 one warp per row, 1 warp specialised with column blocks, 2 warp
+    specialised with slot x column tiles, 3 = 1 with the Z pieces staged by TMA bulk copies) do the same FMAs in the same order: outputs agree to rounding of the epilogue,
     on a graph with isolated rows, rows longer than one stage (> 16 / > 32 in-edges) and more than 16 active slots."""
     from bikg_graph_explainability_public_b200.engine import GraphSpec, MaskedForward
     from bikg_graph_explainability_public_b200.lowering import lower
@@ -499,13 +500,14 @@ def test_layer0_kernel_variants_agree(kind, lib, knobs):
     act = _pack(lib, mask)
     g = GraphSpec(x.cuda(), ei.cuda(), [0, n])
     ys = []
-    for mode in ("0", "1", "2"):
+    for mode in ("0", "1", "2", "3"):
         knobs(l0_ws=int(mode))
         y = MaskedForward(g, lower(arch), [q, 3])(act, s).cpu().numpy()
         np.testing.assert_allclose(y[:, 0], y_ref, rtol=Y_RTOL, atol=Y_ATOL)
         ys.append(y)
     np.testing.assert_allclose(ys[1], ys[0], rtol=2e-6, atol=1e-7)
     np.testing.assert_allclose(ys[2], ys[0], rtol=2e-6, atol=1e-7)
+    np.testing.assert_array_equal(ys[3], ys[1])  # same kernel, another copy engine
 
 
 @pytest.mark.parametrize("name", ["c4_tiny", "c2_wide", "c2_wide2"])
@@ -605,3 +607,43 @@ def test_wlm_fit_matches_closed_form(lib):
             w_dev, losses = fit_surrogate(co, y.cuda(), torch.from_numpy(kern).cuda(), w0.cuda(), params, broadcast)
             np.testing.assert_allclose(w_dev.cpu().numpy(), w_ref.numpy(), atol=2e-5, rtol=1e-3)
             np.testing.assert_allclose(losses, losses_ref, rtol=1e-4, atol=1e-9)
+
+
+@pytest.mark.parametrize("name", ["c3_tenth", "c4_small"])
+def test_parity_at_bench_scale(name, lib, knobs):
+    """The bench workloads at 1/10 (C3: 100 k nodes / 2 M edges, 2 x GCN(128)) and 1/50 (C4: 5 node types / 20 relations /
+    40 k nodes / 1 M edges, 2 x HeteroConv(SAGE)) scale: compact / hetero-compact path, tile path and pruned tile path
+    against the oracle on 8 coalitions of the bench's row family incl. an all-off row, an all-on row and rows in which the
+    query node is inactive.  Bar: 1e-4 relative (BASELINE.json north_star, fp32)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from bikg_graph_explainability_public_b200.data import khop_subgraph
+    from bikg_graph_explainability_public_b200.engine import MaskedForward
+    from bikg_graph_explainability_public_b200.lowering import lower
+
+    wl = bench.Workload(name)
+    dev = torch.device("cuda", 0)
+    arch, eng = wl.engine(dev, "fp32")
+    q = wl.queries[0]
+    mask = bench.make_masks(8, wl.n, wl.c, wl.com_of, 77, wl.com_of2).bool()
+    mask[1] = False
+    mask[2] = True
+    mask[3, q] = False
+    mask[4, q] = True
+    assert (~mask[:, q]).sum() >= 2 and mask[:, q].sum() >= 2
+    y_ref = wl.oracle_eval(wl.oracle_model(arch), mask.numpy())
+    act = _pack(lib, mask)
+
+    def rel(y):
+        return float(np.max(np.abs(y - y_ref) / np.maximum(np.abs(y_ref), 1e-6)))
+
+    y = eng(act, 8)[:, 0].cpu().numpy()
+    assert rel(y) <= 1e-4, ("compact path", rel(y))
+    hop = khop_subgraph(wl.ei.cuda(), wl.n, q, len(eng.edges_per_layer) + 1)[4]
+    pruned = MaskedForward(eng.graph, lower(arch), [q], prune=True, hop=hop, zero_edge_rule=wl.kind == "hetero_sage")
+    yp = pruned(act, 8)[:, 0].cpu().numpy()
+    assert rel(yp) <= 1e-4, ("pruned tile path", rel(yp))
+    knobs(compact=0)
+    tile = MaskedForward(eng.graph, lower(arch), [q], prune=False, zero_edge_rule=wl.kind == "hetero_sage")
+    yt = tile(act, 8)[:, 0].cpu().numpy()
+    assert rel(yt) <= 1e-4, ("tile path", rel(yt))

@@ -46,6 +46,9 @@ def main():
     ap.add_argument("--queries", type=int, default=2)
     ap.add_argument("--prune", type=int, default=1)
     ap.add_argument("--profile", action="store_true", help="per-category kernel ms of every query (CUDA events, xpgnn_profile)")
+    ap.add_argument("--hostprof", action="store_true", help="cProfile of the last query (run with CUDA_LAUNCH_BLOCKING=1 so that "
+                    "device time is charged to the launching call)")
+    ap.add_argument("--device-inputs", action="store_true", help="feat / edge_index already on the GPU (device convention, SURVEY.md 8b)")
     args = ap.parse_args()
 
     from torch import nn
@@ -85,7 +88,9 @@ def main():
               "l1_lambda": 1e-4, "lr_patience": 10, "seed": 1}  # the reference's config/configs.json
     indeg = torch.bincount(ei[1], minlength=n)
     queries = [int(torch.argmax(indeg))] + torch.randint(0, n, (args.queries,), generator=g).tolist()
-    Explainer.engine_options = dict(prune=bool(args.prune), precision="fp32")
+    Explainer.engine_options = dict(Explainer.engine_options, prune=bool(args.prune), precision="fp32")
+    if args.device_inputs:
+        x, ei = x.cuda(), ei.cuda()
     out = []
     for q in queries[:args.queries]:
         pw = [list(p) for p in pathways]
@@ -108,6 +113,18 @@ def main():
                     "top_community": None if pdf is None or len(pdf) == 0 else str(pdf.index[0]),
                     "score_checksum": None if pdf is None else float(pdf["score"].abs().sum()), "rank": rank, "world": world})
         print(json.dumps(out[-1]), flush=True)
+    if args.hostprof and rank == 0:
+        import cProfile
+        import pstats
+
+        pw = [list(p) for p in pathways]
+        pr = cProfile.Profile()
+        pr.enable()
+        ex = Explainer(x, ei, arch, dict(params), list(names), pw, list(pathway_names))
+        ex.run(names[queries[0]], 1)
+        torch.cuda.synchronize()
+        pr.disable()
+        pstats.Stats(pr, stream=sys.stderr).sort_stats("cumulative").print_stats(45)
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
