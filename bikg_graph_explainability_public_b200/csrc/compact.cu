@@ -509,10 +509,10 @@ __global__ void __launch_bounds__(256) cspmm_long_kernel(const CspmmArgs a) {
 // Sums run in list order (self first), so results do not depend on the schedule.  Rows with more than long_cnt active
 // in-edges stay with cspmm_long_kernel.
 // ------------------------------------------------------------------------------------------
-constexpr int kSegCap = 320;     // stream positions staged per round: >= kLongCompact + 1, so a row never straddles rounds
+constexpr int kSegCap = 320;     // stream positions staged per round; a longer row is summed alone, chunk by chunk
 constexpr int kSegTileLd = 36;   // floats per tile row (144 B: 16-byte aligned, consecutive rows 4 banks apart)
 constexpr int kSegRowwise = 24;  // blocks whose longest row has at most this many entries are staged row by row
-static_assert(kSegCap >= kLongCompact + 1 && kSegCap % 32 == 0, "a row (self + kLongCompact sources) must fit one round");
+static_assert(kSegCap % 32 == 0 && kSegCap >= 128, "staging buffer: whole 32-position steps, room for the 4 x 128-byte partial sums");
 
 __device__ __forceinline__ float4 seg_gather(const char* base, uint32_t word) {  // word = source id | last << 31
   const char* p;
@@ -622,6 +622,37 @@ __global__ void __launch_bounds__(128, OCC) cspmm_seg_kernel(const CspmmArgs a) 
       if (base >= nA) break;  // the remaining rows have no entries
       const uint32_t over = __ballot_sync(0xffffffffu, s_aend[warp][lane] - base > kSegCap) & ~((1u << r_lo) - 1u);
       const int r_hi = over ? __ffs(over) - 1 : 32;
+      if (r_hi == r_lo) {
+        // one row longer than a round (graphs without hub rows have no long-row list, so any length can arrive here): the
+        // four groups sum contiguous quarters of every kSegCap-position chunk, the four partial sums are added in group order
+        const int n_row = s_aend[warp][r_lo] - base;
+        const uint32_t e_row = s_e[warp][r_lo];
+        const int v_row = s_rowv[warp][r_lo];
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int S = 0; S < n_row; S += kSegCap) {
+          const int len = min(kSegCap, n_row - S);
+          for (int i = lane; i < len; i += 32) {
+            const int pos = S + i;
+            ids[i] = (gcn && pos == 0) ? (uint32_t)v_row : (uint32_t)__ldcs(cc + e_row + (uint32_t)(pos - (gcn ? 1 : 0)));
+          }
+          __syncwarp();
+          const int per = (len + 3) >> 2;
+          const int q1 = min((grp + 1) * per, len);
+          for (int q = min(grp * per, len); q < q1; ++q) seg_add(acc, seg_gather(in_c, ids[q]));
+          __syncwarp();
+        }
+        float4* part = reinterpret_cast<float4*>(ids);  // 4 groups x 8 lanes x float4 = 512 bytes of the staging buffer
+        part[grp * 8 + sub] = acc;
+        __syncwarp();
+        if (grp == 0) {
+          float4 tot = part[sub];
+          for (int g = 1; g < 4; ++g) { const float4 pg = part[g * 8 + sub]; tot.x += pg.x; tot.y += pg.y; tot.z += pg.z; tot.w += pg.w; }
+          *reinterpret_cast<float4*>(tile + __popc(nonempty & ((1u << r_lo) - 1u)) * kSegTileLd + sub * 4) = tot;
+        }
+        __syncwarp();
+        r_lo = r_lo + 1;
+        continue;
+      }
       const int len = s_aend[warp][r_hi - 1] - base;
       const int a_l = (lane ? s_aend[warp][lane - 1] : 0) - base;  // start of row `lane` relative to the round
       const bool in_round = lane >= r_lo && lane < r_hi;

@@ -13,7 +13,8 @@ struct Knobs {
   int cw = 32;             // XPGNN_CW: 32 | 16 floats per activation chunk
   int l0_lists = 0;        // XPGNN_L0=lists: list-driven layer 0 instead of the row-outer kernels
   int occ = 8;             // XPGNN_OCC: CTAs / SM of the row-lockstep SpMM
-  int seg = 4;             // XPGNN_SEG: 0 row-lockstep SpMM | 4 / 6 / 8 segmented SpMM with that many gathers in flight per lane
+  int seg = 8;             // XPGNN_SEG: 0 row-lockstep SpMM | 4 / 6 / 8 segmented SpMM with that many gathers in flight per lane
+                           // (measured at C3: 8 at 6 CTAs / SM 11.07 ms per tile, 6 at 6: 11.41, 4 at 8: 13.64, row-lockstep 11.59)
   int seg_occ = 0;         // XPGNN_SEG_OCC: 0 default CTAs / SM of the chosen segmented variant
   int l2_stream = 1;       // XPGNN_L2_STREAM / XPGNN_L2_GATHER: L2 eviction priority of streamed / gathered accesses
   int l2_gather = 0;

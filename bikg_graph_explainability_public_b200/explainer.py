@@ -126,8 +126,10 @@ def verify_lowering(arch, feat_dims, node_type_names=None, edge_type_names=None,
         with torch.no_grad():
             ref = arch(*args)
     except NotImplementedError as ex:
-        if "weight container" in str(ex) or "layers are weight containers" in str(ex):
-            return cands[-1], "unverified: arch is built from weight containers (nn.py), its plan is its definition"
+        # nn.py layers hold weights only, and a Module without a forward (torch: 'missing the required "forward" function')
+        # cannot be called either: there is no black box to compare with, the plan is the model's definition
+        if "weight container" in str(ex) or 'missing the required "forward"' in str(ex):
+            return cands[-1], "unverified: arch cannot be called (weight containers / no forward), its plan is its definition"
         raise
     finally:
         arch.train(was_training)
@@ -299,8 +301,13 @@ class Explainer:
         if self.pathways is not None:
             raw_pathways = Pathways(self.pathways, self.pathway_names)
         (ntn, etn, self.feat, self.edge_index, node_types, edge_types, nptr, eptr, pads) = raw.preprocess_hetero_graph()
-        if node_types is None and self.node_types is not None:
-            raise NotImplementedError("custom node_types on a homogeneous graph (5-arg forward) is not lowered")
+        typed_homo = False
+        if node_types is None and self.node_types is not None:  # explainer.py:365-371: caller-provided type vectors of a
+            node_types = self.node_types.clone()                 # homogenised graph (5-argument forward, model.py:110-112)
+            typed_homo = True
+        if edge_types is None and self.edge_types is not None:
+            edge_types = self.edge_types.clone()
+            typed_homo = True
         self.names, _ = raw.hetero2homo_names(self.names)
         if self.pathways is not None:
             self.pathways, self.pathway_names, ptypes = raw_pathways.hetero2homo(self.problem, nptr, eptr)
@@ -315,7 +322,7 @@ class Explainer:
         sub_feat, sub_ei, sub_names, sub_ind, sub_nt, sub_et = data_class.comp_graph(
             ind, n_hops, self.problem, self.names, node_types, edge_types)
         hop = data_class.last_hop
-        query_flat = int(sub_ind[0])
+        query_flat = hop_query = int(sub_ind[0])  # hop levels are distances to this node
 
         sub_pathway_inds = sub_pathway_names = None
         if self.pathways is not None:
@@ -339,9 +346,15 @@ class Explainer:
         if opts.get("verify", True):  # the plan must be the function the reference would call (model.py:104-112)
             fd = int(sub_feat.shape[1]) if ntn is None else {t: int(sub_feat.shape[1]) - int(pads[i]) for i, t in enumerate(ntn)}
             plan, self.lowering_status = verify_lowering(self.arch, fd, ntn, etn, out_type)
+        if typed_homo:
+            # The reference hands the type vectors to arch.forward and then reads row ``sub_ind`` -- the query's index among
+            # the type-1 nodes (explainer.py:280-284) -- of the full output (wlm.py:435-436).  The engine lowers models whose
+            # plan reproduces arch on the probe graph (i.e. that do not branch on the types) and reads the same row.
+            sub_nt = sub_et = None
+            query_flat = int(sub_ind[0])
         engine = build_engine(sub_feat, sub_ei, self.arch, int(sub_ind[0]), sub_nt, sub_et, ntn, etn, pads,
-                              out_type=out_type, hop=hop, prune=opts["prune"], precision=opts["precision"],
-                              query_flat=query_flat, model=plan)
+                              out_type=out_type, hop=hop if not typed_homo or query_flat == int(hop_query) else None,
+                              prune=opts["prune"], precision=opts["precision"], query_flat=query_flat, model=plan)
         # ---- all repeats' coalitions first: the masks, the surrogate init and the DataLoader seed draw of repeat r + 1
         # depend on the RNG stream only (masks -> randperm -> N init draws -> 2 draws, explainer.py:490-523 / wlm.py:210),
         # never on the predictions, so every repeat's rows go through ONE sharded engine call ----

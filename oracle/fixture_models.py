@@ -44,6 +44,15 @@ class HomoGCN(nn.Module):
         return x
 
 
+class HomoGCN5(HomoGCN):
+    """Same stack behind the reference's 5-argument protocol ``forward(x, edge_index, node_types, edge_types)``
+    (``model.py:110-112``): a model trained on a homogenised hetero graph that receives the type vectors."""
+
+    def forward(self, x, edge_index, node_types, edge_types):
+        assert node_types.shape[0] == x.shape[0] and edge_types.shape[0] == edge_index.shape[1]
+        return super().forward(x, edge_index)
+
+
 class HeteroGCNSingleType(nn.Module):
     """HeteroConv of GCNConv per relation over ONE node type (matches
     ``test_data/gcn_hetero_1hop_lungCancer.pth.tar``)."""
@@ -69,6 +78,14 @@ class HeteroGCNSingleType(nn.Module):
         for l in self.fc:
             x = l(x)
         return x
+
+
+class HeteroGCNSingleTypeDict(HeteroGCNSingleType):
+    """The dict-returning variant (``model.py:255-292``): ``{node type: output}`` instead of the output tensor."""
+
+    def forward(self, x_dict, edge_index_dict):
+        key = list(x_dict.keys())[0]
+        return {key: super().forward(x_dict, edge_index_dict)}
 
 
 class HeteroSAGE(nn.Module):

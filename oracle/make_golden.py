@@ -145,6 +145,31 @@ def build_cases():
     cases.append(dict(name="c4_hetero_sage", feat=featd, edge_index=eid, names=namesd, pathways=comd,
                       pathway_names=comn, params=p5, model=spec5, state=None, element="ge7", times=1,
                       problem="node_prediction", element_type="gene", patch_multitype=True))
+    # f2: the 5-argument protocol forward(x, edge_index, node_types, edge_types) (model.py:110-112) on a homogenised graph
+    # with caller-provided type vectors (explainer.py:365-371); the query index is taken among the type-1 nodes
+    # (explainer.py:280-284) and then used as a row of the full output (wlm.py:435-436) -- reproduced as is
+    g = torch.Generator().manual_seed(4321)
+    n5, e5, f5 = 150, 900, 16
+    feat5 = torch.randn(n5, f5, generator=g)
+    ei5 = torch.randint(0, n5, (2, e5), generator=g)
+    names5 = ["v%d" % i for i in range(n5)]
+    nt5 = (torch.arange(n5) % 3 != 0).float()          # node type 1 for two thirds of the nodes (incl. the query)
+    et5 = torch.randint(0, 4, (e5,), generator=g).float()
+    perm5 = torch.randperm(n5, generator=g).tolist()
+    coms5 = [[names5[i] for i in perm5[j::5]] for j in range(5)]
+    spec6 = dict(cls="HomoGCN5", in_dim=f5, conv_dims=[16, 16], head_dims=[16, 1], seed=9)
+    p6 = dict(PARAMS, interpret_samples=10, epochs=8, seed=5)
+    cases.append(dict(name="gcn2_5arg", feat=feat5, edge_index=ei5, names=names5, pathways=coms5,
+                      pathway_names=["k%d" % j for j in range(5)], params=p6, model=spec6, state=None, element="v7",
+                      times=1, problem="node_prediction", element_type=None, node_types=nt5, edge_types=et5))
+    # f2: dict-returning hetero arch (model.py:255-292), single node type, C2 inputs
+    spec7 = dict(cls="HeteroGCNSingleTypeDict", in_dim=84, relations=[list(r) for r in rels],
+                 conv_dims=[16], head_dims=[16, 16, 32, 1])
+    cases.append(dict(name="c2_dict_out", feat={"gene": cap["feat"]}, edge_index=ei_dict,
+                      names={"gene": cap["names"]}, pathways={"gene": cap["pathways"]},
+                      pathway_names={"gene": cap["pathway_names"]}, params=dict(cap["params"]),
+                      model=spec7, state=het_sd, element="10", times=1, problem="node_prediction",
+                      element_type="gene"))
     return cases
 
 
@@ -207,7 +232,7 @@ def run_case(case):
     try:
         ex = Explainer(fresh(case["feat"]), fresh(case["edge_index"]), arch, dict(case["params"]),
                        fresh(case["names"]), fresh(case["pathways"]), fresh(case["pathway_names"]),
-                       case["element_type"], case["problem"])
+                       case["element_type"], case["problem"], fresh(case.get("node_types")), fresh(case.get("edge_types")))
         cfg, pdf = ex.run(case["element"], case["times"])
     finally:
         rec.close()
@@ -218,7 +243,8 @@ def run_case(case):
     o = orc.explain(fresh(case["feat"]), fresh(case["edge_index"]), arch, dict(case["params"]),
                     fresh(case["names"]), fresh(case["pathways"]), fresh(case["pathway_names"]),
                     case["element_type"], case["problem"], element=case["element"],
-                    times=case["times"], mt=mt)
+                    times=case["times"], mt=mt, node_types=fresh(case.get("node_types")),
+                    edge_types=fresh(case.get("edge_types")))
 
     # ---- oracle port vs reference (pins the oracle) ----
     sub_feat, sub_ei, sub_names, sub_ind, _, _ = rec.comp_graph[0]
@@ -276,6 +302,9 @@ def save_case(case, o, cfg, pdf, state, rng_blob):
     else:
         d["feat"] = _flat(case["feat"])
         d["edge_index"] = _flat(case["edge_index"])
+        if case.get("node_types") is not None:
+            d["node_types"] = _flat(case["node_types"])
+            d["edge_types"] = _flat(case["edge_types"])
         meta["names"] = case["names"]
         meta["pathways"] = case["pathways"]
         meta["pathway_names"] = case["pathway_names"]
@@ -384,15 +413,19 @@ def kernel_goldens():
 
 def main():
     os.makedirs(OUT, exist_ok=True)
+    only = set(sys.argv[1:])  # optional: names of the cases to (re)generate; the unit goldens only without arguments
     for case in build_cases():
+        if only and case["name"] not in only:
+            continue
         o, cfg, pdf, state, blob = run_case(case)
         path = save_case(case, o, cfg, pdf, state, blob)
         r0 = o["runs"][0]
         print("golden", case["name"], "N_sub", len(o["subset"]), "E_sub", o["sub_edge_index"].shape[1],
               "rows", r0["mask"].shape[0], "B", r0["batch_size"], "y", tuple(r0["batches"][0][2].shape),
               "->", os.path.basename(path), os.path.getsize(path) // 1024, "KiB")
-    mask_stream_goldens()
-    kernel_goldens()
+    if not only:
+        mask_stream_goldens()
+        kernel_goldens()
 
 
 if __name__ == "__main__":

@@ -261,6 +261,12 @@ def shap_kernel(mask):
 # a6/a7  black-box inference on the block-diagonal batch       model.py:62-328, wlm.py:284-438
 
 
+def _forward_arity(arch):
+    import inspect
+
+    return len(inspect.getfullargspec(arch.forward).args)  # model.py:104 (getargspec there)
+
+
 def _unique_types(t):
     return torch.unique(t)
 
@@ -291,6 +297,9 @@ def kernel_output(mask, feat, edge_index, arch, q, node_type=None, edge_type=Non
                 ei_dict = {nm: pei_t[:, torch.where(pet_t == i)[0]].long()
                            for i, nm in enumerate(edge_type_names)}
                 out = arch(x_dict, ei_dict)
+            elif node_type is not None and edge_type is not None and _forward_arity(arch) == 5:
+                # model.py:110-112: homogenised hetero graph, the model takes the replicated type vectors as well
+                out = arch(concat, pei_t, torch.hstack([node_type] * b), torch.from_numpy(pet))
             else:
                 out = arch(concat, pei_t)
             if isinstance(out, dict):  # model.py:255-292
@@ -454,7 +463,8 @@ def flatten_hetero(feat, edge_index):
 
 
 def explain(feat, edge_index, arch, params, names, pathways=None, pathway_names=None,
-            element_type=None, problem="node_prediction", element=None, times=1, mt=None):
+            element_type=None, problem="node_prediction", element=None, times=1, mt=None,
+            node_types=None, edge_types=None):
     """Port of ``Explainer.run`` for node problems.  Returns a dict of every intermediate.
 
     ``mt``: an MT19937 positioned where torch's CPU generator would be; defaults to the
@@ -488,6 +498,10 @@ def explain(feat, edge_index, arch, params, names, pathways=None, pathway_names=
     if pathways is not None and pathway_names is None:
         pathway_names = list(range(len(pathways)))
 
+    if ntypes is None and node_types is not None:  # explainer.py:365-371: caller-provided type vectors
+        ntypes = node_types.clone()
+    if etypes is None and edge_types is not None:
+        etypes = edge_types.clone()
     assert "graph" not in problem and "edge" not in problem, "oracle covers node problems"
     hops = get_num_hops(arch)
     if etn is not None:
@@ -506,6 +520,9 @@ def explain(feat, edge_index, arch, params, names, pathways=None, pathway_names=
     if element_type is not None:  # explainer.py:451-463
         t = ntn.index(element_type)
         filt = np.array(sub_names, dtype=str)[(sub_nt == t).numpy()].tolist()
+        sub_ind = int(np.where(np.array(filt, dtype=str) == element)[0][0])
+    elif node_types is not None or edge_types is not None:  # explainer.py:280-284: "that element with node type 1"
+        filt = np.array(sub_names, dtype=str)[(sub_nt == 1).numpy()].tolist()
         sub_ind = int(np.where(np.array(filt, dtype=str) == element)[0][0])
 
     n_sub = sub_feat.shape[0]

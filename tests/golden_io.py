@@ -6,7 +6,8 @@ import numpy as np
 import torch
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = ["c1_homo_gcn", "c1_homo_gcn_times3", "c2_hetero_gcn", "gcn2_random", "sage2_shapley", "c4_hetero_sage"]
+CASES = ["c1_homo_gcn", "c1_homo_gcn_times3", "c2_hetero_gcn", "gcn2_random", "sage2_shapley", "c4_hetero_sage",
+         "gcn2_5arg", "c2_dict_out"]
 
 
 def load_case(name):
@@ -19,6 +20,9 @@ def load_case(name):
     else:
         case["feat"] = torch.from_numpy(z["feat"])
         case["edge_index"] = torch.from_numpy(z["edge_index"])
+        if "node_types" in z.files:  # 5-argument protocol: caller-provided type vectors (explainer.py:83-84)
+            case["node_types"] = torch.from_numpy(z["node_types"])
+            case["edge_types"] = torch.from_numpy(z["edge_types"])
     case["state"] = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w::")}
     return case
 

@@ -35,7 +35,9 @@ def _run_product(case, prune):
     arch = gio.build_arch(case)
     if "rng_state" in case["z"].files:
         torch.set_rng_state(torch.from_numpy(case["z"]["rng_state"].copy()))
-    ex = Explainer(feat, ei, arch, dict(meta["params"]), names, pathways, pnames, meta["element_type"], meta["problem"])
+    nt, et = case.get("node_types"), case.get("edge_types")
+    ex = Explainer(feat, ei, arch, dict(meta["params"]), names, pathways, pnames, meta["element_type"], meta["problem"],
+                   None if nt is None else nt.clone(), None if et is None else et.clone())
     ex.options = dict(prune=prune, keep_last=True)
     cfg, pdf = ex.run(meta["element"], meta["times"])
     return ex, cfg, pdf

@@ -24,7 +24,8 @@ def test_oracle_explain_matches_reference_golden(name):
     mt = MT19937.from_torch_state(z["rng_state"]) if "rng_state" in z.files else None
     o = orc.explain(copy.deepcopy(case["feat"]), copy.deepcopy(case["edge_index"]), arch, dict(meta["params"]), names,
                     pathways, pnames, meta["element_type"], meta["problem"], element=meta["element"],
-                    times=meta["times"], mt=mt)
+                    times=meta["times"], mt=mt, node_types=copy.deepcopy(case.get("node_types")),
+                    edge_types=copy.deepcopy(case.get("edge_types")))
     assert np.array_equal(o["subset"], z["subset"]) and np.array_equal(o["sub_edge_index"], z["sub_edge_index"])
     assert o["sub_ind"] == int(z["sub_ind"])
     for r, run in enumerate(o["runs"]):
