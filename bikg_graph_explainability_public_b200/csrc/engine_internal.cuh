@@ -1,5 +1,7 @@
 // Host-side helpers shared by the two forward drivers (engine.cu: tile path, compact.cu: compact path).
 #pragma once
+#include <nvtx3/nvToolsExt.h>
+
 #include <vector>
 
 #include "common.cuh"
@@ -20,10 +22,18 @@ struct Profile {
   }
 };
 extern Profile g_prof;
+// Every engine stage is also an NVTX range (nvtx3 is header-only: no extra library), so a timeline tool shows
+// masked degree / compaction / layer-0 SpMM / layer >= 1 SpMM / dense transform / head per tile.
+inline const char* prof_name(int cat) {
+  static const char* const names[PROF_N] = {"xpgnn:masked_degree", "xpgnn:spmm_invariant_l0", "xpgnn:spmm_tile_l1", "xpgnn:dense",
+                                            "xpgnn:head", "xpgnn:compaction"};
+  return cat >= 0 && cat < PROF_N ? names[cat] : "xpgnn";
+}
 struct ProfScope {
   cudaStream_t st;
   cudaEvent_t stop = nullptr;
   ProfScope(int cat, cudaStream_t s) : st(s) {
+    nvtxRangePushA(prof_name(cat));
     if (!g_prof.on) return;
     cudaEvent_t a, b;
     cudaEventCreate(&a);
@@ -32,7 +42,10 @@ struct ProfScope {
     g_prof.ev[cat].push_back({a, b});
     stop = b;
   }
-  ~ProfScope() { if (stop) cudaEventRecord(stop, st); }
+  ~ProfScope() {
+    if (stop) cudaEventRecord(stop, st);
+    nvtxRangePop();
+  }
 };
 
 // bump allocator over the caller's workspace (base == nullptr: size query)

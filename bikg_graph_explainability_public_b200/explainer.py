@@ -297,6 +297,8 @@ class Explainer:
             raise NotImplementedError("graph / edge problems are outside the accelerated path (SURVEY.md 8f-4)")
         if times == 1:
             set_seed(self.params["seed"])
+        nvtx = torch.cuda.nvtx
+        nvtx.range_push("xpgnn:run:flatten")
         raw = Data(self.feat, self.edge_index)
         if self.pathways is not None:
             raw_pathways = Pathways(self.pathways, self.pathway_names)
@@ -313,6 +315,8 @@ class Explainer:
             self.pathways, self.pathway_names, ptypes = raw_pathways.hetero2homo(self.problem, nptr, eptr)
             pathway_class = Pathways(self.pathways, self.pathway_names, ptypes)
 
+        nvtx.range_pop()
+        nvtx.range_push("xpgnn:run:khop")
         self.feat = self.feat.to(dev)
         self.edge_index = self.edge_index.to(dev)
         data_class = Data(self.feat, self.edge_index)
@@ -324,6 +328,8 @@ class Explainer:
         hop = data_class.last_hop
         query_flat = hop_query = int(sub_ind[0])  # hop levels are distances to this node
 
+        nvtx.range_pop()
+        nvtx.range_push("xpgnn:run:communities")
         sub_pathway_inds = sub_pathway_names = None
         if self.pathways is not None:
             # pathways.py:33-136 (comp_graph + names2inds) in one vectorised pass; see Pathways.resolve_indices
@@ -336,6 +342,8 @@ class Explainer:
             sub_ind = torch.tensor([self.extract_index(element, filtered)])
         del self.feat, self.edge_index  # explainer.py:476: the object is single use
 
+        nvtx.range_pop()
+        nvtx.range_push("xpgnn:run:engine_build")
         elements = int(sub_feat.shape[0])
         opts = dict(type(self).engine_options)
         opts.update(getattr(self, "options", {}))
@@ -358,6 +366,8 @@ class Explainer:
         # ---- all repeats' coalitions first: the masks, the surrogate init and the DataLoader seed draw of repeat r + 1
         # depend on the RNG stream only (masks -> randperm -> N init draws -> 2 draws, explainer.py:490-523 / wlm.py:210),
         # never on the predictions, so every repeat's rows go through ONE sharded engine call ----
+        nvtx.range_pop()
+        nvtx.range_push("xpgnn:run:masks")
         sync_rng_across_ranks()
         sets = []
         for _ in range(times):
@@ -371,7 +381,11 @@ class Explainer:
             act_all = torch.cat([c.act for c, _ in sets], dim=1).contiguous()
             n_all = 32 * int(act_all.shape[1])
         check_ranks_agree(act_all)
+        nvtx.range_pop()
+        nvtx.range_push("xpgnn:run:masked_forward")
         y_all = sharded_eval(engine, act_all, n_all)[:, 0]
+        nvtx.range_pop()
+        nvtx.range_push("xpgnn:run:fit")
         config_vals, word0 = [], 0
         for coalitions, w0 in sets:
             y = y_all[32 * word0: 32 * word0 + coalitions.n_coalitions]
@@ -385,9 +399,12 @@ class Explainer:
             if opts.get("keep_last", False):  # tests / debugging only: pins the coalition draws and predictions in HBM
                 self._last = dict(coalitions=coalitions, y=y, kernel=kern, w0=w0, subset_names=sub_names,
                                   sub_edge_index=sub_ei, sub_ind=query_flat)
+        nvtx.range_pop()
+        nvtx.range_push("xpgnn:run:aggregate")
         mean, std = self.weight_stacking(config_vals)
         config_val_df = Data.config_val_dataframe(mean, std, sub_names)
         pathway_df = None
         if self.pathways is not None:
             pathway_df = sub_pathway_class.aggregate(mean, sub_pathway_inds)
+        nvtx.range_pop()
         return config_val_df, pathway_df

@@ -52,3 +52,36 @@ def test_sharded_eval_world2():
         out = mgr.dict()
         mp.spawn(_worker, args=(2, _free_port(), n_coalitions, out), nprocs=2, join=True)
         assert out[0] and out[1], n_coalitions
+
+
+def _rng_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from bikg_graph_explainability_public_b200.explainer import check_ranks_agree, sync_rng_across_ranks
+
+    torch.manual_seed(100 + rank)  # the usual "seed + rank" pattern: ranks would draw different coalition masks
+    sync_rng_across_ranks()         # rank 0's generator becomes authoritative (times > 1 does not re-seed, explainer.py:342)
+    draws = torch.randint(0, 2 ** 31 - 1, (40, 3), dtype=torch.int64).to(torch.int32)
+    gathered = [torch.empty_like(draws) for _ in range(world)]
+    dist.all_gather(gathered, draws)
+    same_stream = all(torch.equal(g, gathered[0]) for g in gathered)
+    check_ranks_agree(draws)        # identical coalition matrices: passes
+    act = draws.clone()
+    if rank == 1:
+        act[7, 1] ^= 4              # one coalition bit differs on one rank
+    try:
+        check_ranks_agree(act)
+        raised = False
+    except RuntimeError:
+        raised = True
+    out[rank] = (same_stream, raised)
+    dist.destroy_process_group()
+
+
+def test_ranks_replay_one_coalition_stream_world2():
+    """Explainer.run under one process per GPU: every rank generates the coalition masks itself, so the CPU generators must
+    agree (rank 0's state is broadcast) and a divergence must raise instead of pairing predictions with wrong rows."""
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_rng_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert out[0] == (True, True) and out[1] == (True, True)
