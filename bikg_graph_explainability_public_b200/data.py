@@ -106,7 +106,8 @@ class Data:
             else:
                 sub_names = np.array(names, dtype=str)[idx].tolist()
         else:
-            raise NotImplementedError("edge problems are outside the accelerated path (SURVEY.md 8f-4)")
+            raise NotImplementedError("edge problems: the reference raises here as well (ind_filter is undefined for "
+                                      "homogeneous graphs, data.py:359)")
         return sub_feat, sub_ei, sub_names, sub_ind, sub_nt, sub_et
 
     def element_size(self, problem):

@@ -293,8 +293,11 @@ class Explainer:
         """explainer.py:316-546.  Returns (config_val_df, pathway_df)."""
         dev = require_cuda()
         _lib.load()
-        if "graph" in self.problem or "edge" in self.problem:
-            raise NotImplementedError("graph / edge problems are outside the accelerated path (SURVEY.md 8f-4)")
+        if "edge" in self.problem:
+            # the reference itself cannot run them: comp_graph raises UnboundLocalError on homogeneous graphs (data.py:359,
+            # ``ind_filter``), Mask reads an attribute that is never set (masks.py:294, ``self.edge_size``)
+            raise NotImplementedError("edge problems: the reference path is not runnable (data.py:359, masks.py:294); not built")
+        graph_problem = "graph" in self.problem
         if times == 1:
             set_seed(self.params["seed"])
         nvtx = torch.cuda.nvtx
@@ -323,21 +326,35 @@ class Explainer:
         relations = len(etn) if etn is not None else 0
         n_hops = Model(self.arch).get_hops(relations)
         ind = self.extract_index(element, self.names)
-        sub_feat, sub_ei, sub_names, sub_ind, sub_nt, sub_et = data_class.comp_graph(
-            ind, n_hops, self.problem, self.names, node_types, edge_types)
-        hop = data_class.last_hop
+        if graph_problem:
+            # explainer.py:427-447: no computational-graph cut -- the whole graph, every community as given, the prediction
+            # read at the element's own row (wlm.py:435-436); every conv layer runs over the whole graph ("full" mode)
+            sub_feat, sub_ei, sub_names = self.feat, self.edge_index.to(torch.int64), self.names
+            sub_ind = torch.tensor([ind])
+            sub_nt = None if node_types is None else node_types.to(dev)
+            sub_et = None if edge_types is None else edge_types.to(dev)
+            hop = None
+        else:
+            sub_feat, sub_ei, sub_names, sub_ind, sub_nt, sub_et = data_class.comp_graph(
+                ind, n_hops, self.problem, self.names, node_types, edge_types)
+            hop = data_class.last_hop
         query_flat = hop_query = int(sub_ind[0])  # hop levels are distances to this node
 
         nvtx.range_pop()
         nvtx.range_push("xpgnn:run:communities")
         sub_pathway_inds = sub_pathway_names = None
-        if self.pathways is not None:
+        if self.pathways is not None and graph_problem:  # explainer.py:447-449, 464-470: communities kept as given
+            sub_pathway_names = self.pathway_names
+            first = self.pathways[0][0]
+            sub_pathway_inds = Pathways(self.pathways, sub_pathway_names).names2inds(sub_names) if isinstance(first, str) else self.pathways
+            sub_pathway_class = Pathways(sub_pathway_inds, sub_pathway_names)
+        elif self.pathways is not None:
             # pathways.py:33-136 (comp_graph + names2inds) in one vectorised pass; see Pathways.resolve_indices
             sub_pathway_inds, sub_pathway_names = pathway_class.resolve_indices(sub_names)
             if not sub_pathway_inds:
                 raise IndexError("list index out of range")  # explainer.py:467: no community reaches the computational graph
             sub_pathway_class = Pathways(sub_pathway_inds, sub_pathway_names)
-        if self.element_type is not None or self.node_types is not None or self.edge_types is not None:
+        if not graph_problem and (self.element_type is not None or self.node_types is not None or self.edge_types is not None):
             filtered = self.filter_hetero_names(sub_names, sub_nt, sub_et, ntn, etn)
             sub_ind = torch.tensor([self.extract_index(element, filtered)])
         del self.feat, self.edge_index  # explainer.py:476: the object is single use

@@ -193,7 +193,7 @@ class Mask:
 
     def mask_generator(self):
         if "edge" in self.problem:
-            raise NotImplementedError("edge-level coalitions are outside the accelerated path (SURVEY.md 8f-4)")
+            raise NotImplementedError("edge-level coalitions: the reference reads self.edge_size, which is never set (masks.py:294)")
         feat = self.feat
         if isinstance(feat, dict):
             n = sum(int(t.shape[0]) for t in feat.values())

@@ -145,6 +145,11 @@ def build_cases():
     cases.append(dict(name="c4_hetero_sage", feat=featd, edge_index=eid, names=namesd, pathways=comd,
                       pathway_names=comn, params=p5, model=spec5, state=None, element="ge7", times=1,
                       problem="node_prediction", element_type="gene", patch_multitype=True))
+    # f4: graph problem (explainer.py:427-447): no k-hop cut, the whole graph is the computational graph, all communities kept
+    cases.append(dict(name="gcn2_graph", feat=feat[:120], edge_index=ei[:, (ei[0] < 120) & (ei[1] < 120)], names=names[:120],
+                      pathways=[[names[i] for i in c if i < 120] for c in coms[:7]],
+                      pathway_names=["com%d" % i for i in range(7)], params=dict(PARAMS, interpret_samples=10, epochs=9, seed=8),
+                      model=spec3, state=None, element="n17", times=1, problem="graph_prediction", element_type=None))
     # f2: the 5-argument protocol forward(x, edge_index, node_types, edge_types) (model.py:110-112) on a homogenised graph
     # with caller-provided type vectors (explainer.py:365-371); the query index is taken among the type-1 nodes
     # (explainer.py:280-284) and then used as a row of the full output (wlm.py:435-436) -- reproduced as is
@@ -247,9 +252,10 @@ def run_case(case):
                     edge_types=fresh(case.get("edge_types")))
 
     # ---- oracle port vs reference (pins the oracle) ----
-    sub_feat, sub_ei, sub_names, sub_ind, _, _ = rec.comp_graph[0]
-    assert np.array_equal(o["sub_edge_index"], sub_ei.numpy())
-    assert o["sub_names"] == sub_names
+    if rec.comp_graph:  # graph problems never cut a computational graph
+        sub_feat, sub_ei, sub_names, sub_ind, _, _ = rec.comp_graph[0]
+        assert np.array_equal(o["sub_edge_index"], sub_ei.numpy())
+        assert o["sub_names"] == sub_names
     assert len(rec.masks) == case["times"]
     bi = 0
     for r, run in enumerate(o["runs"]):

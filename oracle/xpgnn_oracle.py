@@ -502,22 +502,31 @@ def explain(feat, edge_index, arch, params, names, pathways=None, pathway_names=
         ntypes = node_types.clone()
     if etypes is None and edge_types is not None:
         etypes = edge_types.clone()
-    assert "graph" not in problem and "edge" not in problem, "oracle covers node problems"
+    assert "edge" not in problem, "the reference itself raises on edge problems of homogeneous graphs (data.py:359)"
     hops = get_num_hops(arch)
     if etn is not None:
         hops //= len(etn)
     ind = int(np.where(np.array(names, dtype=str) == element)[0][0])
     ei_np = edge_index.numpy() if isinstance(edge_index, torch.Tensor) else np.asarray(edge_index)
-    subset, sub_ei, sub_ind, edge_mask = k_hop_subgraph(ei_np, ind, hops + 1)
+    if "graph" in problem:  # explainer.py:427-447: no computational-graph cut, every community kept as given
+        subset, sub_ei, sub_ind = np.arange(feat.shape[0]), ei_np.astype(np.int64), ind
+        edge_mask = np.ones(ei_np.shape[1], dtype=bool)
+    else:
+        subset, sub_ei, sub_ind, edge_mask = k_hop_subgraph(ei_np, ind, hops + 1)
     sub_feat = feat[torch.from_numpy(subset)]
     sub_names = np.array(names, dtype=str)[subset].tolist()
     sub_nt = ntypes[torch.from_numpy(subset)] if ntypes is not None else None
     sub_et = etypes[torch.from_numpy(np.flatnonzero(edge_mask))] if etypes is not None else None
     sub_p = sub_pn = sub_pi = None
     if pathways is not None:
-        sub_p, sub_pn, _ = communities_in_subgraph(pathways, pathway_names, sub_names)
-        sub_pi = names_to_indices(sub_p, sub_names)
-    if element_type is not None:  # explainer.py:451-463
+        if "graph" in problem:
+            sub_p, sub_pn = pathways, pathway_names
+        else:
+            sub_p, sub_pn, _ = communities_in_subgraph(pathways, pathway_names, sub_names)
+        sub_pi = names_to_indices(sub_p, sub_names) if isinstance(sub_p[0][0], str) else sub_p  # explainer.py:467-470
+    if "graph" in problem:
+        pass  # explainer.py:451: no per-type index filtering for graph problems
+    elif element_type is not None:  # explainer.py:451-463
         t = ntn.index(element_type)
         filt = np.array(sub_names, dtype=str)[(sub_nt == t).numpy()].tolist()
         sub_ind = int(np.where(np.array(filt, dtype=str) == element)[0][0])

@@ -7,7 +7,7 @@ import torch
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = ["c1_homo_gcn", "c1_homo_gcn_times3", "c2_hetero_gcn", "gcn2_random", "sage2_shapley", "c4_hetero_sage",
-         "gcn2_5arg", "c2_dict_out"]
+         "gcn2_5arg", "c2_dict_out", "gcn2_graph"]
 
 
 def load_case(name):
