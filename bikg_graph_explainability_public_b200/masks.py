@@ -86,7 +86,9 @@ def generate_coalitions(n_elements, communities, params, device=None):
     st = _lib.stream_ptr()
 
     if communities is None:  # Shapley mode (masks.py:231-260, 362-365)
-        draws = stream.draw(total * n + max(total - 1, 0))
+        snap0 = stream.snapshot()
+        n_draws = total * n + max(total - 1, 0)
+        draws = stream.draw(n_draws)
         ind = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
         _lib.check(lib.xpgnn_randperm(draws.data_ptr() + 4 * total * n, total, ind.data_ptr(), st))
         stream.hand_back()
@@ -97,10 +99,14 @@ def generate_coalitions(n_elements, communities, params, device=None):
                                             pop.data_ptr(), st))
 
         def expand():
+            # the draws (one int32 per mask bit) are not kept alive: the dense view replays them from the saved state
+            d = stream.replay(snap0, n_draws)
             m = torch.empty((total, n), dtype=torch.uint8, device=dev)
-            _lib.check(lib.xpgnn_shapley_expand(draws.data_ptr(), ind.data_ptr(), total, n, m.data_ptr(), None, w,
+            _lib.check(lib.xpgnn_shapley_expand(d.data_ptr(), ind.data_ptr(), total, n, m.data_ptr(), None, w,
                                                 None, _lib.stream_ptr()))
             return m.bool()
+
+        del draws
 
         if total < epochs:
             raise ValueError("batch_size should be a positive integer value, but got batch_size=0")
@@ -163,10 +169,13 @@ def generate_coalitions(n_elements, communities, params, device=None):
                                      act.data_ptr(), w, prow.data_ptr(), pop.data_ptr(), st))
 
     def expand():
+        d = stream.replay(snap, used)  # see the Shapley branch: draws are replayed, not kept
         m = torch.empty((n_out, n), dtype=torch.uint8, device=dev)
-        _lib.check(lib.xpgnn_mask_expand(C.byref(mp), draws.data_ptr(), offsets.data_ptr(), ind.data_ptr(), n_out,
+        _lib.check(lib.xpgnn_mask_expand(C.byref(mp), d.data_ptr(), offsets.data_ptr(), ind.data_ptr(), n_out,
                                          m.data_ptr(), None, w, None, None, _lib.stream_ptr()))
         return m.bool()
+
+    del draws
 
     expand._keep = keep  # the plan's device arrays must outlive the closure
     if n_out < epochs:

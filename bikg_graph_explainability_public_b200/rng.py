@@ -42,6 +42,14 @@ class DeviceStream:
                                                _lib.stream_ptr()))
         return out
 
+    def replay(self, snap, n):
+        """The ``n`` draws that followed ``snap`` (a ``snapshot()``), without disturbing the live stream."""
+        keep = self.snapshot()
+        self.restore(snap)
+        out = self.draw(n)
+        self.restore(keep)
+        return out
+
     def hand_back(self):
         """Write the advanced state into torch's CPU generator (``torch.set_rng_state``)."""
         words = self.state.cpu().numpy().view(np.uint32).astype(np.uint64)
