@@ -23,7 +23,9 @@ struct Knobs {
   int occ16 = 8;           // XPGNN_OCC16
   int l0_multi = 1;        // XPGNN_L0_MULTI
   int l1_multi = 0;        // XPGNN_L1_MULTI
-  int l0_ws = 1;           // XPGNN_L0_WS: 0 one warp per row | 1 warp specialised | 2 slot x column tiling
+  int l0_ws = 3;           // XPGNN_L0_WS: 0 one warp per row | 1 warp specialised, cp.async staging | 2 slot x column tiling |
+                           // 3 (default) = 1 with the Z pieces staged by TMA bulk copies (UBLKCP): same arithmetic, bit-identical;
+                           // measured at C3 4.91 vs 4.93 ms per tile, R-MAT 10.27 vs 10.32 (profiles/r02_summary.md)
   int dense_simt = 0;      // XPGNN_DENSE=simt: exact fp32 FMA transforms instead of 3xTF32 tensor-core products
   int prune_l0 = 1;        // XPGNN_PRUNE_L0
   int fused = 0;           // XPGNN_FUSED

@@ -128,7 +128,7 @@ def generate_coalitions(n_elements, communities, params, device=None):
     n_pos, rows = len(visited), int(sum(sizes))
     row_start = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
     com_ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
-    flat = np.fromiter((v for p in communities for v in sorted(p)), dtype=np.int64, count=int(com_ptr[-1]))
+    flat = (np.concatenate([np.sort(np.asarray(p, dtype=np.int64)) for p in communities]) if c else np.zeros(0, dtype=np.int64))
     if flat.size and (flat.min() < 0 or flat.max() >= n):
         raise IndexError("community member outside [0, %d)" % n)
     com_of = np.repeat(np.arange(c, dtype=np.int32), lens)

@@ -82,25 +82,23 @@ class Pathways:
         return inds
 
     def resolve_indices(self, names):
-        """``comp_graph`` + ``names2inds`` in one vectorised pass, for ``Explainer.run``: the communities with at least one
-        member among ``names`` as lists of subgraph indices (first occurrence of each name, duplicates collapsed -- what
+        """``comp_graph`` + ``names2inds`` in one pass, for ``Explainer.run``: the communities with at least one member among
+        ``names`` as lists of subgraph indices (first occurrence of each name, duplicates collapsed -- what
         ``np.intersect1d(..., return_indices=True)`` yields, pathways.py:84-96,131-134), plus their names.  The lists are in
         ascending index order instead of lexicographic name order: ``Mask.mask_generator`` sorts them numerically in place
-        before anything reads them (masks.py:323), and the community mean does not depend on the order."""
+        before anything reads them (masks.py:323), and the community mean does not depend on the order.
+        One name -> first-index dict, then per community a C-level key-view intersection and a numeric sort (measured
+        against a vectorised numpy / pandas join over all members: 0.35 s vs 0.6 s at 564 k names / 1 M members -- the
+        cost is hashing scattered Python strings either way)."""
         first = _first_index(names)
-        n = len(names)
-        lens = np.fromiter(map(len, self.communities), dtype=np.int64, count=len(self.communities))
-        flat = list(itertools.chain.from_iterable(self.communities))
-        flat = _as_str(flat)
-        idx = np.fromiter(map(first.get, flat, itertools.repeat(-1)), dtype=np.int64, count=len(flat))
-        com = np.repeat(np.arange(len(lens), dtype=np.int64), lens)
-        keep = idx >= 0
-        key = np.unique(com[keep] * max(n, 1) + idx[keep])
-        com_u, idx_u = key // max(n, 1), key % max(n, 1)
-        counts = np.bincount(com_u, minlength=len(lens))
-        parts = np.split(idx_u, np.cumsum(counts)[:-1]) if len(lens) else []
-        inds = [p.tolist() for p, c in zip(parts, counts) if c > 0]
-        kept = [nm for nm, c in zip(self.community_names, counts) if c > 0]
+        keys = first.keys()
+        lookup = first.__getitem__
+        inds, kept = [], []
+        for community, cname in zip(self.communities, self.community_names):
+            common = keys & set(_as_str(community))
+            if common:
+                inds.append(sorted(map(lookup, common)))
+                kept.append(cname)
         return inds, kept
 
     def shift_hetero_pathways(self, pointers):
