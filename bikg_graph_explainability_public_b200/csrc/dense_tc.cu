@@ -132,7 +132,10 @@ constexpr int TC_THREADS = 32 * (EPI_WARPS + LOADER_WARPS + 1);  // warps 0-7 ep
 constexpr int MAX_DONE = 12;      // lcm(stages <= 4, LOADER_GROUPS)
 constexpr int KC = 32;           // K elements per stage
 constexpr int MAX_STAGES = 4;
-constexpr int TR_STRIDE = 20;     // floats per row of a 32 x 16 transposition block (16-byte aligned, conflict-free writes)
+constexpr int TR_STRIDE = 16;     // floats per row of a 32 x 16 transposition block; the four 16-byte groups of row r sit at
+                                  // group ^ ((r >> 1) & 3): conflict-free row writes AND conflict-free transposed reads (the padded
+                                  // stride of round 1 made half of the reads two-wavefront: r02 ncu, 84 M of 163 M LDS wavefronts)
+__device__ __forceinline__ int tr_off(int row, int group) { return row * TR_STRIDE + ((group ^ ((row >> 1) & 3)) << 2); }
 
 // MODE 0: TF32x3 (element 4 B, hi/lo copies)   MODE 1: BF16 (element 2 B)
 template <int MODE>
@@ -184,13 +187,13 @@ __device__ __noinline__ float4 sigmoid4(float4 v) {
   return v;
 }
 // row-per-thread fallback for outputs that cannot be written as float4: `row16` = the thread's 16 accumulators in shared memory
-__device__ __noinline__ void scalar_epilogue(const float* row16, int c0, int n_out, const float* s_bias, float* out_row, int cw_out, int cw_out_lg,
+__device__ __noinline__ void scalar_epilogue(const float* row16, int swz, int c0, int n_out, const float* s_bias, float* out_row, int cw_out, int cw_out_lg,
                                              int64_t out_chunk_stride, int accumulate, int act_fn, float rs) {
 #pragma unroll 1
   for (int c = 0; c < 16; ++c) {
     const int n = c0 + c;
     if (n >= n_out) break;
-    float x = row16[c] + s_bias[n];
+    float x = row16[(((c >> 2) ^ swz) << 2) | (c & 3)] + s_bias[n];  // 16-byte groups are stored XOR-swizzled (tr_off)
     float* op = out_row + (cw_out ? (int64_t)(n >> cw_out_lg) * out_chunk_stride + (n & (cw_out - 1)) : (int64_t)n);
     if (accumulate) x += *op;
     *op = apply_act(x, act_fn) * rs;
@@ -474,7 +477,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const DenseArgs
         __syncwarp();
 #pragma unroll
         for (int c = 0; c < 16; c += 4)
-          *reinterpret_cast<uint4*>(s_t + lane * TR_STRIDE + c) = make_uint4(r[c], r[c + 1], r[c + 2], r[c + 3]);
+          *reinterpret_cast<uint4*>(s_t + tr_off(lane, c >> 2)) = make_uint4(r[c], r[c + 1], r[c + 2], r[c + 3]);
         __syncwarp();
         if (vec_ok) {
           const int cq = (lane & 3) * 4, n = c0 + cq;
@@ -483,7 +486,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const DenseArgs
             const int64_t ooff = dense_out_off(a, n);
             float4 v[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const float4*>(s_t + (i * 8 + (lane >> 2)) * TR_STRIDE + cq);
+            for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const float4*>(s_t + tr_off(i * 8 + (lane >> 2), lane & 3));
             if (a.accumulate && !a.out16) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
@@ -515,7 +518,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const DenseArgs
             }
           }
         } else if (ok) {
-          scalar_epilogue(s_t + lane * TR_STRIDE, c0, a.n_out, s_bias, a.out + oo, a.cw_out, a.cw_out_lg, a.out_chunk_stride, a.accumulate,
+          scalar_epilogue(s_t + lane * TR_STRIDE, (lane >> 1) & 3, c0, a.n_out, s_bias, a.out + oo, a.cw_out, a.cw_out_lg, a.out_chunk_stride, a.accumulate,
                           a.act_fn, rs);
         }
       }
