@@ -758,6 +758,245 @@ __global__ void __launch_bounds__(128, OCC) cspmm_seg_kernel(const CspmmArgs a) 
 }
 
 // ------------------------------------------------------------------------------------------
+// Segmented masked SpMM, shared-memory ring variant.  The register-queue kernel above is latency bound (r02 ncu: 7.5 of
+// 9.4 warp-cycles per issue stalled on the long scoreboard, 8.3 TB/s through the fabric): what it can keep in flight is
+// what its registers hold (24 warps x 4 groups x 8 row pieces = 98 KB per SM).  Here the gathers are cp.async copies
+// (LDGSTS, 16 bytes per lane = one 128-byte row piece per group) into a per-group ring of R slots in shared memory, so
+// the data in flight is bounded by shared memory instead: 16 warps x 4 groups x 24 slots = 196 KB per SM.  A lane reads
+// back exactly the 16 bytes it copied (cp.async.wait_group orders a thread's own copies), accumulates, and refills the
+// slot R positions ahead.  Finished rows are scaled and stored straight from registers.  Same stream, same cut at row
+// boundaries, same summation order as cspmm_seg_kernel: bit-identical results.
+// ------------------------------------------------------------------------------------------
+constexpr int kRingWarps = 4;
+template <int R>
+struct RingSmem {
+  float4 ring[kRingWarps][4][R][8];   // [warp][group][slot][lane of the group]: 16 bytes each
+  uint32_t ids[kRingWarps][kSegCap];
+  int rowv[kRingWarps][32];           // per block row: node id | -1
+  int aend[kRingWarps][32];
+  uint32_t e[kRingWarps][32];
+  uint32_t cnt[kRingWarps][32];
+  int outv[kRingWarps][32];           // k-th non-empty row of the block: node id and scale (the order rows close in)
+  float outs[kRingWarps][32];
+  int next[kRingWarps][2];
+  int start[33];
+  int nact[32];
+};
+
+template <int R, int OCC>
+__global__ void __launch_bounds__(32 * kRingWarps, OCC) cspmm_ring_kernel(const CspmmArgs a) {
+  extern __shared__ __align__(16) uint8_t ring_smem_raw[];
+  RingSmem<R>& S = *reinterpret_cast<RingSmem<R>*>(ring_smem_raw);
+  if (threadIdx.x <= a.nb) S.start[threadIdx.x] = a.slot_tile_start[threadIdx.x];
+  if (threadIdx.x < a.nb) S.nact[threadIdx.x] = a.slot_info[threadIdx.x].x;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane & 7, grp = lane >> 3;
+  const int total = S.start[a.nb] * a.n_chunks * 4;
+  const bool gcn = a.kind == XPGNN_CONV_GCN;
+  uint32_t* ids = S.ids[warp];
+  const uint32_t ring_base = (uint32_t)__cvta_generic_to_shared(&S.ring[warp][grp][0][sub]);  // slot stride: 8 x 16 bytes
+
+  int t_cur = 0;
+  auto grab = [&]() {
+    int it = 0;
+    if (lane == 0) it = atomicAdd(a.counter, 1);
+    return __shfl_sync(0xffffffffu, it, 0);
+  };
+  auto load_meta = [&](int item, int& v, uint32_t& e, uint32_t& f) {
+    v = -1; e = 0; f = 0;
+    if (item >= total) return;
+    const int idx = item >> 2;
+    while (idx >= S.start[t_cur + 1] * a.n_chunks) ++t_cur;
+    const int ntb = S.start[t_cur + 1] - S.start[t_cur];
+    const int rem = idx - S.start[t_cur] * a.n_chunks;
+    const int c = rem / ntb;
+    const int row0 = (rem - c * ntb) * 128 + (item & 3) * 32;
+    if (lane == 0) { S.next[warp][0] = t_cur; S.next[warp][1] = c; }
+    const int i = row0 + lane;
+    if (i < S.nact[t_cur]) {
+      v = __ldcs(a.act_list + (int64_t)t_cur * a.N + i);
+      const uint32_t* rp = a.rowptr_c + (int64_t)t_cur * (a.N + 1) + i;
+      e = __ldcs(rp);
+      f = __ldcs(rp + 1);
+    }
+  };
+  int item1 = grab();
+  int v1;
+  uint32_t e1, f1;
+  load_meta(item1, v1, e1, f1);
+  int item2 = grab();
+
+  while (item1 < total) {
+    __syncwarp();
+    const int t = S.next[warp][0], c = S.next[warp][1];
+    __syncwarp();
+    int nA, n_l, v_l;
+    uint32_t e_l, nonempty;
+    float* out_c = a.out + (int64_t)t * a.out_s_stride + (int64_t)c * a.out_chunk_stride + sub * 4;
+    {
+      const uint32_t cnt_l = f1 - e1;
+      const bool is_long = a.long_cnt > 0 && cnt_l > (uint32_t)a.long_cnt;
+      const bool mine = v1 >= 0 && !is_long;
+      n_l = mine ? (int)cnt_l + (gcn ? 1 : 0) : 0;
+      v_l = v1; e_l = e1;
+      int a_end = n_l;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, a_end, o);
+        if (lane >= o) a_end += y;
+      }
+      S.rowv[warp][lane] = mine ? v1 : -1;
+      S.aend[warp][lane] = a_end;
+      S.e[warp][lane] = e1;
+      S.cnt[warp][lane] = cnt_l;
+      nA = __shfl_sync(0xffffffffu, a_end, 31);
+      nonempty = __ballot_sync(0xffffffffu, n_l > 0);
+      if (n_l > 0) {  // rows close in this order
+        const int k = __popc(nonempty & ((1u << lane) - 1u));
+        S.outv[warp][k] = v1;
+        S.outs[warp][k] = gcn ? gcn_dinv(cnt_l) : 1.0f / (float)cnt_l;
+      }
+      // SAGE: a row without an active in-edge aggregates to zero and has no stream entry
+      uint32_t empties = __ballot_sync(0xffffffffu, mine && n_l == 0);
+      while (empties) {
+        const int r = __ffs(empties) - 1;
+        empties &= empties - 1;
+        const int vr = __shfl_sync(0xffffffffu, v1, r);
+        if (lane < 8) __stcs(reinterpret_cast<float4*>(out_c + (int64_t)vr * 32), make_float4(0.f, 0.f, 0.f, 0.f));  // lane < 8: sub = lane
+      }
+      item1 = item2;
+      load_meta(item1, v1, e1, f1);
+      item2 = grab();
+    }
+    const int n_max = __reduce_max_sync(0xffffffffu, n_l);
+    __syncwarp();
+    const int32_t* cc = a.ccol + a.slot_base[t];
+    const char* in_c = reinterpret_cast<const char*>(a.in + (int64_t)t * a.in_s_stride + (int64_t)c * a.in_chunk_stride + sub * 4);
+
+    int r_lo = 0;
+    while (r_lo < 32) {
+      const int base = r_lo ? S.aend[warp][r_lo - 1] : 0;
+      if (base >= nA) break;
+      const uint32_t over = __ballot_sync(0xffffffffu, S.aend[warp][lane] - base > kSegCap) & ~((1u << r_lo) - 1u);
+      int r_hi = over ? __ffs(over) - 1 : 32;
+      int len, lone_len = 0;
+      uint32_t lone_e = 0;
+      int lone_v = 0;
+      const bool lone = r_hi == r_lo;  // one row longer than a round: streamed alone, chunk by chunk, by group 0 .. 3 in quarters
+      if (lone) {
+        lone_len = S.aend[warp][r_lo] - base; lone_e = S.e[warp][r_lo]; lone_v = S.rowv[warp][r_lo];
+        r_hi = r_lo + 1;
+      }
+      const int a_l = (lane ? S.aend[warp][lane - 1] : 0) - base;
+      const bool in_round = lane >= r_lo && lane < r_hi;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      int trow = __popc(nonempty & ((1u << r_lo) - 1u));
+      for (int S0 = 0; S0 < (lone ? lone_len : 1); S0 += kSegCap) {
+        if (lone) {
+          len = min(kSegCap, lone_len - S0);
+          for (int i = lane; i < len; i += 32) {
+            const int pos = S0 + i;
+            ids[i] = ((gcn && pos == 0) ? (uint32_t)lone_v : (uint32_t)__ldcs(cc + lone_e + (uint32_t)(pos - (gcn ? 1 : 0)))) |
+                     (pos == lone_len - 1 ? 0x80000000u : 0u);
+          }
+        } else {
+          len = S.aend[warp][r_hi - 1] - base;
+          if (n_max <= kSegRowwise) {
+            if (in_round && n_l > 0) {
+              int o = a_l;
+              if (gcn) ids[o++] = (uint32_t)v_l | (n_l == 1 ? 0x80000000u : 0u);
+              const int ne = n_l - (gcn ? 1 : 0);
+              for (int k = 0; k < ne; ++k) ids[o + k] = (uint32_t)__ldg(cc + e_l + k) | (k == ne - 1 ? 0x80000000u : 0u);
+            }
+          } else {
+            for (int i = lane; i < len; i += 32) {
+              const int pos = base + i;
+              int r = 0;
+#pragma unroll
+              for (int step = 16; step >= 1; step >>= 1)
+                if (S.aend[warp][r + step - 1] <= pos) r += step;
+              const int ar = r ? S.aend[warp][r - 1] : 0;
+              int id;
+              if (gcn) id = pos == ar ? S.rowv[warp][r] : __ldcs(cc + S.e[warp][r] + (uint32_t)(pos - ar - 1));
+              else id = __ldcs(cc + S.e[warp][r] + (uint32_t)(pos - ar));
+              ids[i] = (uint32_t)id | (pos == S.aend[warp][r] - 1 ? 0x80000000u : 0u);
+            }
+          }
+        }
+        // pieces: at row boundaries (several rows) or plain quarters of the chunk (one long row; partial sums are combined below)
+        const int per = (len + 3) >> 2;
+        int q = min(grp * per, len), q1 = min((grp + 1) * per, len);
+        if (!lone) {
+          q = 0; q1 = len;
+#pragma unroll
+          for (int g = 1; g < 4; ++g) {
+            const uint32_t m = __ballot_sync(0xffffffffu, in_round && n_l > 0 && a_l >= g * per);
+            const int first = m ? __ffs(m) - 1 : 32;
+            const int start = m ? __shfl_sync(0xffffffffu, a_l, first & 31) : len;
+            if (grp == g) { q = start; trow = __popc(nonempty & ((1u << (first & 31)) - 1u)); }
+            if (grp == g - 1) q1 = start;
+          }
+        }
+        __syncwarp();
+        // ---- stream through the ring: the copy of position p lands in slot p % R ----
+        const int steps = __reduce_max_sync(0xffffffffu, q1 - q);
+        int slot_w = 0;  // slot the next issued copy goes to
+#pragma unroll 1
+        for (int k = 0; k < R; ++k) {  // prologue: fill the ring (one committed group per position, empty groups past the end)
+          if (q + k < q1) {
+            const char* src;
+            asm("mad.wide.u32 %0, %1, 128, %2;" : "=l"(src) : "r"(ids[q + k] & 0x7fffffffu), "l"(in_c));
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring_base + (uint32_t)k * 128u), "l"(src) : "memory");
+          }
+          asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        int slot_r = 0;
+#pragma unroll 1
+        for (int k = 0; k < steps; ++k) {
+          asm volatile("cp.async.wait_group %0;" ::"n"(R - 1) : "memory");  // the oldest of this thread's R pending copies has landed
+          const int p = q + k;
+          if (p < q1) {
+            float4 x;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(ring_base + (uint32_t)slot_r * 128u) : "memory");
+            const uint32_t wk = ids[p];
+            seg_add(acc, x);
+            if (p + R < q1) {
+              const char* src;
+              asm("mad.wide.u32 %0, %1, 128, %2;" : "=l"(src) : "r"(ids[p + R] & 0x7fffffffu), "l"(in_c));
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring_base + (uint32_t)slot_r * 128u), "l"(src) : "memory");
+            }
+            if ((int)wk < 0 && !lone) {  // the row ends here: scale and store it
+              const float sc = S.outs[warp][trow];
+              __stcs(reinterpret_cast<float4*>(out_c + (int64_t)S.outv[warp][trow] * 32), make_float4(acc.x * sc, acc.y * sc, acc.z * sc, acc.w * sc));
+              ++trow;
+              acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+          asm volatile("cp.async.commit_group;" ::: "memory");
+          slot_r = slot_r + 1 == R ? 0 : slot_r + 1;
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        (void)slot_w;
+      }
+      if (lone) {  // the four partial sums of the long row, added in group order
+        float4* part = reinterpret_cast<float4*>(ids);
+        part[grp * 8 + sub] = acc;
+        __syncwarp();
+        if (grp == 0) {
+          float4 tot = part[sub];
+          for (int g = 1; g < 4; ++g) { const float4 pg = part[g * 8 + sub]; tot.x += pg.x; tot.y += pg.y; tot.z += pg.z; tot.w += pg.w; }
+          const float sc = S.outs[warp][trow];
+          __stcs(reinterpret_cast<float4*>(out_c + (int64_t)S.outv[warp][trow] * 32), make_float4(tot.x * sc, tot.y * sc, tot.z * sc, tot.w * sc));
+        }
+        __syncwarp();
+      }
+      r_lo = r_hi;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // layers >= 1 of a HeteroConv(sum), transform-first: Z_r = H W_r^T has been computed per relation over the active
 // rows of its source type; this kernel gathers, per destination row, over the compacted lists of ALL relations into
 // the destination type, adds the merged root term and bias, applies the activation and writes the row ONCE
@@ -1143,7 +1382,20 @@ static int launch_cspmm(const CspmmArgs& a, int cw, cudaStream_t st) {
   const int seg = knobs().seg;  // 0: row-lockstep kernel | 4 / 6 / 8: gathers in flight per lane
   if (seg > 0 && cw == 32 && a.counter && !a.wgt && !a.addend && !a.bias && !a.layer0 && !a.prescale && a.act_fn == XPGNN_ACT_NONE) {
     const int socc = knobs().seg_occ;
-    if (seg >= 8) k = socc == 8 ? cspmm_seg_kernel<8, 8> : cspmm_seg_kernel<8, 6>;
+    if (seg >= 100) {  // shared-memory ring variant: seg = 100 + slots per group (116 | 124)
+      void (*kr)(const CspmmArgs) = seg >= 124 ? cspmm_ring_kernel<24, 4> : cspmm_ring_kernel<16, 5>;
+      const int smem = seg >= 124 ? (int)sizeof(RingSmem<24>) : (int)sizeof(RingSmem<16>);
+      XP_CHECK(cudaFuncSetAttribute(kr, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      int per_sm = 0;
+      XP_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kr, 32 * kRingWarps, smem));
+      ProfScope ps(a.prof_cat > 0 ? a.prof_cat : PROF_SPMM_TILE, st);
+      XP_LAUNCH(kr, kNumSMs * std::max(per_sm, 1), 32 * kRingWarps, smem, st, a);
+      if (a.long_cnt > 0) XP_LAUNCH((cspmm_long_kernel<32, false>), kNumSMs * 8, 256, 0, st, a);
+      return 0;
+    }
+    if (seg >= 16) k = cspmm_seg_kernel<16, 4>;       // 16 warps / SM x 16 gathers in flight per lane (128 registers)
+    else if (seg >= 12) k = cspmm_seg_kernel<12, 5>;  // 20 warps / SM x 12
+    else if (seg >= 8) k = socc == 8 ? cspmm_seg_kernel<8, 8> : cspmm_seg_kernel<8, 6>;
     else if (seg >= 6) k = socc == 6 ? cspmm_seg_kernel<6, 6> : cspmm_seg_kernel<6, 8>;
     else k = socc == 10 ? cspmm_seg_kernel<4, 10> : cspmm_seg_kernel<4, 8>;
     int per_sm = 0;

@@ -376,10 +376,11 @@ def test_compact_path_hub_rows(kind, lib, knobs):
 
 
 @pytest.mark.parametrize("kind", ["gcn", "sage"])
-@pytest.mark.parametrize("seg", ["0", "4", "6", "8"])
+@pytest.mark.parametrize("seg", ["0", "4", "6", "8", "12", "16", "116", "124"])
 def test_segmented_spmm_variants(kind, seg, lib, knobs):
     """Layers >= 1 through the segmented SpMM (cspmm_seg_kernel: a warp sums the gather stream of a 32-row block in four
-    contiguous pieces) with 4 / 6 / 8 gathers in flight per lane, and through the row-lockstep kernel (0): medium hubs
+    pieces cut at row boundaries) with 4 .. 16 gathers in flight per lane, through its shared-memory ring variant (116 / 124:
+    cp.async into 16 / 24 slots per group) and through the row-lockstep kernel (0): medium hubs
     (80-240 active in-edges, below the long-row threshold) make blocks longer than one staging round, rows cut by piece
     and round boundaries, empty rows (SAGE) and a short last block; vs the oracle, bitwise repeatable."""
     from bikg_graph_explainability_public_b200.engine import GraphSpec, MaskedForward
