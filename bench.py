@@ -625,8 +625,16 @@ def main():
     y_pad = torch.zeros((s_max, nq), dtype=torch.float32, device=dev)
     y_all = torch.empty((world * s_max, nq), dtype=torch.float32, device=dev)
 
-    def forward(bits):
+    compute_events = []  # (start, stop) around the rank's own masked forward, without the collective
+
+    def forward(bits, record=False):
+        if record:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         y = eng(bits, s_local)
+        if record:
+            e1.record()
+            compute_events.append((e0, e1))
         if world > 1:
             y_pad[:s_local] = y
             dist.all_gather_into_tensor(y_all, y_pad)  # the single collective of the path
@@ -655,16 +663,18 @@ def main():
         barrier()
         ev0.record()
         for _ in range(args.steps):
-            y = forward(act)
+            y = forward(act, record=True)
         ev1.record()
         barrier()
     ms_rank = float(ev0.elapsed_time(ev1))
-    ms_all = torch.tensor([ms_rank], device=dev)
-    ms_ranks = [ms_rank]
+    compute_rank = float(sum(a.elapsed_time(b) for a, b in compute_events))
+    ms_all = torch.tensor([ms_rank, compute_rank], device=dev)
+    ms_ranks, compute_ranks = [ms_rank], [compute_rank]
     if world > 1:
-        gathered = [torch.zeros(1, device=dev) for _ in range(world)]
+        gathered = [torch.zeros(2, device=dev) for _ in range(world)]
         dist.all_gather(gathered, ms_all)
-        ms_ranks = [float(g.item()) for g in gathered]
+        ms_ranks = [float(g[0].item()) for g in gathered]
+        compute_ranks = [float(g[1].item()) for g in gathered]
     ms_total = max(ms_ranks)
     launches = _lib.launch_count() - launches0
     active_visits = torch.tensor([float((eng.stats.cpu() - stats0)[1])], device=dev)  # active edge visits of this rank
@@ -751,6 +761,8 @@ def main():
             "masked_gteps": value / nq * visits / 1e9,
             "active_gteps": float(active_visits.item()) / (ms_total / 1e3) / 1e9,  # edges that are active in their coalition
             "ms_per_step_by_rank": [m / args.steps for m in ms_ranks],
+            # the rank's own masked forward without the all-gather: shows the straggler the collective then waits for
+            "compute_ms_per_step_by_rank": [m / args.steps for m in compute_ranks],
             "e2e": {"value": evals / e2e_total, "unit": "coalition evals/s",
                     "h2d_bytes_per_step": int(act_host.numel() * 4), "d2h_bytes_per_step": int(y_host.numel() * 4),
                     "input": "packed coalition matrix [N][W] uint32 (the C ABI's input format) in pinned host memory"},
