@@ -52,6 +52,8 @@ WORKLOADS = {
     "c2_100k": dict(kind="hetero_gcn1", nodes=100_000, edges=2_000_000, features=84, hidden=16, communities=50, relations=3),
     # C3 with 10 % of the nodes in a second community (overlapping communities)
     "c3_overlap": dict(kind="homo_gcn", nodes=1_000_000, edges=20_000_000, features=128, hidden=128, communities=500, overlap=0.1),
+    # half of C3 at the same degree: its per-pass gather working set is 32 MB instead of 64 MB (L2 experiment, profiles/r02_summary.md)
+    "c3_half": dict(kind="homo_gcn", nodes=500_000, edges=10_000_000, features=128, hidden=128, communities=250),
     "c3_tenth": dict(kind="homo_gcn", nodes=100_000, edges=2_000_000, features=128, hidden=128, communities=50),
     "c4_small": dict(kind="hetero_sage", nodes=40_000, edges=1_000_000, features=64, hidden=128, communities=40,
                      type_frac=(0.4, 0.25, 0.15, 0.1, 0.1), relations=20),
