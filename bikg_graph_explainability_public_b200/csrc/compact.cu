@@ -303,30 +303,7 @@ __device__ __forceinline__ void st_hint4(float* ptr, const float4& v, uint64_t p
 // the whole GPU works on one (slot, chunk) pass (+- skew) whose gathered operand fits in L2.
 // A row is owned by CW/4 lanes (float4 each); a warp advances 32/(CW/4) rows together.
 // ------------------------------------------------------------------------------------------
-struct CspmmArgs {
-  int nb, N, n_chunks, kind, layer0, act_fn, prescale;  // layer0: the self term is weighted by deg^-1/2 as well (operand not pre-scaled)
-  int prof_cat;               // -1: by layer0
-  const int2* slot_info;
-  const int32_t* slot_tile_start;
-  const int32_t* act_list;    // [nb][N]
-  const uint32_t* rowptr_c;   // [nb][N+1]
-  const long long* slot_base; // [nb] first entry of the slot's list in ccol
-  const int32_t* ccol;
-  const float* in;            // chunk-major operand, rows by original node id
-  int64_t in_s_stride;        // 0: coalition invariant (layer 0)
-  int64_t in_chunk_stride;
-  const float* wgt;           // [nb][N] per-source weight (layer-0 GCN) or NULL
-  const float* addend;        // chunk-major coalition-invariant addend or NULL
-  int64_t add_chunk_stride;
-  const float* bias;          // per-column addend or NULL
-  int32_t* counter;           // work counter (zeroed per launch); NULL: static round-robin
-  int long_cnt;               // compact rows with more active in-edges are left to cspmm_long_kernel (0: none)
-  const int32_t* long_list;   // entries slot << 26 | compact row, written by compact_finalize_kernel
-  const int32_t* n_long_list;
-  int l2_stream, l2_gather;   // eviction priority of the streamed / gathered accesses (l2_policy kinds)
-  float* out;
-  int64_t out_s_stride, out_chunk_stride;
-};
+// (CspmmArgs lives in compact_internal.cuh: compact_bulk.cu launches over the same lists)
 
 // finishes one row piece (CW / 4 lanes x float4): normalisation, self term, addend, activation, pre-scale, store
 template <int CW>
@@ -1384,6 +1361,12 @@ static int launch_cspmm(const CspmmArgs& a, int cw, cudaStream_t st) {
   const int seg = knobs().seg;  // 0: row-lockstep kernel | 4 / 6 / 8: gathers in flight per lane
   if (seg > 0 && cw == 32 && a.counter && !a.wgt && !a.addend && !a.bias && !a.layer0 && !a.prescale && a.act_fn == XPGNN_ACT_NONE) {
     const int socc = knobs().seg_occ;
+    if (seg >= 200) {  // warp-specialised TMA bulk-copy variant (compact_bulk.cu): seg = 200 + ring stages (216 | 232 | 248)
+      ProfScope ps(a.prof_cat > 0 ? a.prof_cat : PROF_SPMM_TILE, st);
+      if (launch_cspmm_bulk(a, seg - 200, st)) return 1;
+      if (a.long_cnt > 0) XP_LAUNCH((cspmm_long_kernel<32, false>), kNumSMs * 8, 256, 0, st, a);
+      return 0;
+    }
     if (seg >= 100) {  // shared-memory ring variant: seg = 100 + slots per group (116 | 124)
       void (*kr)(const CspmmArgs) = seg >= 124 ? cspmm_ring_kernel<24, 4> : cspmm_ring_kernel<16, 5>;
       const int smem = seg >= 124 ? (int)sizeof(RingSmem<24>) : (int)sizeof(RingSmem<16>);

@@ -77,6 +77,36 @@ struct L0MultiArgs {
   int row_lo, row_hi;
 };
 
+// Arguments of the list-driven masked SpMM kernels of the compact path (compact.cu: row-lockstep / segmented / ring
+// variants; compact_bulk.cu: the warp-specialised TMA bulk-copy variant).
+struct CspmmArgs {
+  int nb, N, n_chunks, kind, layer0, act_fn, prescale;  // layer0: the self term is weighted by deg^-1/2 as well (operand not pre-scaled)
+  int prof_cat;               // -1: by layer0
+  const int2* slot_info;
+  const int32_t* slot_tile_start;
+  const int32_t* act_list;    // [nb][N]
+  const uint32_t* rowptr_c;   // [nb][N+1]
+  const long long* slot_base; // [nb] first entry of the slot's list in ccol
+  const int32_t* ccol;
+  const float* in;            // chunk-major operand, rows by original node id
+  int64_t in_s_stride;        // 0: coalition invariant (layer 0)
+  int64_t in_chunk_stride;
+  const float* wgt;           // [nb][N] per-source weight (layer-0 GCN) or NULL
+  const float* addend;        // chunk-major coalition-invariant addend or NULL
+  int64_t add_chunk_stride;
+  const float* bias;          // per-column addend or NULL
+  int32_t* counter;           // work counter (zeroed per launch); NULL: static round-robin
+  int long_cnt;               // compact rows with more active in-edges are left to cspmm_long_kernel (0: none)
+  const int32_t* long_list;   // entries slot << 26 | compact row, written by compact_finalize_kernel
+  const int32_t* n_long_list;
+  int l2_stream, l2_gather;   // eviction priority of the streamed / gathered accesses (l2_policy kinds)
+  float* out;
+  int64_t out_s_stride, out_chunk_stride;
+};
+
+// layers >= 1, aggregate-first: warp-specialised kernel whose gathers are TMA bulk copies into a shared-memory ring (compact_bulk.cu)
+int launch_cspmm_bulk(const CspmmArgs& a, int variant, cudaStream_t st);
+
 // ---- launchers of compact_l0.cu (return non-zero on a CUDA error, like every launch helper of the engine) ----
 // rows that are not hub rows: warp specialised by default (XPGNN_L0_WS selects the variant)
 int launch_l0_rows(const L0RowsArgs& r, bool sigmoid, bool out16, int n_rows, cudaStream_t st);
