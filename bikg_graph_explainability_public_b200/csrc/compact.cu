@@ -1361,7 +1361,7 @@ static int launch_cspmm(const CspmmArgs& a, int cw, cudaStream_t st) {
   const int seg = knobs().seg;  // 0: row-lockstep kernel | 4 / 6 / 8: gathers in flight per lane
   if (seg > 0 && cw == 32 && a.counter && !a.wgt && !a.addend && !a.bias && !a.layer0 && !a.prescale && a.act_fn == XPGNN_ACT_NONE) {
     const int socc = knobs().seg_occ;
-    if (seg >= 200) {  // warp-specialised TMA bulk-copy variant (compact_bulk.cu): seg = 200 + ring stages (216 | 232 | 248)
+    if (seg >= 200) {  // warp-specialised TMA bulk-copy variant (compact_bulk.cu): seg = 200 + 100 * mode + ring stages (16 | 32): 216 / 232 bulk copies, 316 / 332 cp.async.cg, 432 cp.async.ca, 516 / 532 TMA gather4
       ProfScope ps(a.prof_cat > 0 ? a.prof_cat : PROF_SPMM_TILE, st);
       if (launch_cspmm_bulk(a, seg - 200, st)) return 1;
       if (a.long_cnt > 0) XP_LAUNCH((cspmm_long_kernel<32, false>), kNumSMs * 8, 256, 0, st, a);
@@ -1386,7 +1386,28 @@ static int launch_cspmm(const CspmmArgs& a, int cw, cudaStream_t st) {
     int per_sm = 0;
     XP_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, 128, 0));
     ProfScope ps(a.prof_cat > 0 ? a.prof_cat : PROF_SPMM_TILE, st);
-    XP_LAUNCH(k, kNumSMs * std::max(per_sm, 1), 128, 0, st, a);
+    if (knobs().seg_tma) {
+      // Hybrid: the small TMA gather4 kernel goes first on a second stream (one CTA per SM), the register-queue kernel fills
+      // the rest of every SM; both take 32-row blocks from a.counter in order, so the TMA unit's bytes per cycle add to the
+      // LSU path's.  Fork / join with events: everything after this call on `st` sees both kernels finished.
+      static cudaStream_t aux = nullptr;
+      static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+      if (!aux) {
+        int prio_lo = 0, prio_hi = 0;  // highest priority: its CTAs are placed before the register-queue kernel's
+        XP_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        XP_CHECK(cudaStreamCreateWithPriority(&aux, cudaStreamNonBlocking, prio_hi));
+        XP_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        XP_CHECK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+      }
+      XP_CHECK(cudaEventRecord(ev_fork, st));
+      XP_CHECK(cudaStreamWaitEvent(aux, ev_fork, 0));
+      if (launch_cspmm_bulk(a, 400 + 16, aux)) return 1;
+      XP_LAUNCH(k, kNumSMs * std::max(per_sm - 1, 1), 128, 0, st, a);  // one CTA less per SM: room for the gather4 kernel's registers
+      XP_CHECK(cudaEventRecord(ev_join, aux));
+      XP_CHECK(cudaStreamWaitEvent(st, ev_join, 0));
+    } else {
+      XP_LAUNCH(k, kNumSMs * std::max(per_sm, 1), 128, 0, st, a);
+    }
     if (a.long_cnt > 0) XP_LAUNCH((cspmm_long_kernel<32, false>), kNumSMs * 8, 256, 0, st, a);
     return 0;
   }

@@ -1,38 +1,46 @@
 // Masked SpMM of layers >= 1 (aggregate-first: unweighted sums of pre-scaled 128-byte row pieces, out = scale * sum),
-// warp-specialised: the gathers are ASYNCHRONOUS COPIES into a shared-memory ring (TMA bulk copies or cp.async), so the data
-// in flight is bounded by shared memory instead of registers and the load issue is decoupled from the arithmetic.
+// warp-specialised: the gathers are ASYNCHRONOUS COPIES into a shared-memory ring, so the data in flight is bounded by
+// shared memory instead of registers and the load issue is decoupled from the arithmetic.
 //
-// STATUS: opt-in (option seg = 2xx / 3xx / 4xx), bit-identical to cspmm_seg_kernel and covered by the parity tests, but
-// SLOWER on B200 -- 20.5 ms per C3 tile with cp.async, 35.6 ms with bulk copies, against 11.1 ms for the register-queue
-// kernel.  The role cycle counters (make EXPERIMENTS=1, XPGNN_BG_DBG=1) and tools/tma_gather4_probe.cu say why: for 128-byte
-// rows the asynchronous copy engines are slower than LDG.128 -- LDGSTS moves 16 bytes per cycle per SM (one 16-byte lane
-// request per cycle), a per-lane cp.async.bulk (UBLKCP takes its operands from uniform registers, so a warp issues its 32
-// copies one by one) 9 - 15, and the TMA gather4 form (UTMALDG.2D.GATHER4, 4 rows per instruction) 29.7 = 8.4 TB/s per GPU,
-// TMA-unit bound (same rate from a 16 MB table) -- against > 40 bytes per cycle per SM for plain LDG.128
-// (tools/gather_probe.cu, 11.3 TB/s).  profiles/r02_summary.md section 1b has the numbers.  Kept as the measured answer
-// to "stage the gathered feature rows through TMA": on this part the register path is the fast one.
+// What the copy engines of this SM deliver for 128-byte rows (measured; profiles/r02_summary.md section 1b,
+// tools/tma_gather4_probe.cu): LDGSTS (cp.async) 16 bytes per cycle per SM -- one 16-byte lane request per cycle;
+// per-lane cp.async.bulk (UBLKCP takes its operands from uniform registers, so a warp issues its 32 copies one by one)
+// 9 - 15; the TMA gather4 form (UTMALDG.2D.GATHER4: 4 rows of a 2-D tensor map per instruction, row indices in registers)
+// 29.7 = 8.4 TB/s per GPU, TMA-unit bound; plain LDG.128 > 40 (11.3 TB/s in tools/gather_probe.cu).  Alone, this kernel is
+// therefore SLOWER than the register-queue kernel (cspmm_seg_kernel, compact.cu): 19 - 36 ms per C3 tile against 11.1.
+// But the register-queue kernel is not fabric bound either -- it is short of registers for gathers in flight -- and the TMA
+// unit is idle while it runs.  MODE 3 (gather4) is built to run NEXT TO it: both kernels take 32-row blocks from the same
+// in-order work counter, this one with few warps and no register queue, so the TMA unit adds its bytes per cycle to those of
+// the LSU path (launch_cspmm, option seg_tma).  Sums run in stream order in both kernels: results do not depend on which
+// kernel took a block.
 //
-//   * one SCHEDULER warp takes 128-row items (slot, chunk, row tile) IN ORDER from the global work counter (the whole GPU
-//     stays inside one (slot, chunk) pass, whose gathered operand fits L2), loads the item's row ids / list offsets -- two
-//     items ahead of their use -- and publishes a descriptor in shared memory: per row the inclusive end of its part of
-//     the gather STREAM (for GCN the row itself first -- the operands are pre-scaled by deg^-1/2, so the unit self loop is
-//     one more unweighted term -- then its active sources in list order), the row id and its first list entry;
-//   * kBgProd PRODUCER warps walk the stream 32 positions (= one ring stage) at a time, across item boundaries, with the
-//     source ids of their next three stages already loading: lane = position, its row by binary search over the row ends,
-//     its source id from the compacted list; then either ONE bulk copy per lane (mode 0: cp.async.bulk = the TMA unit,
-//     SASS UBLKCP, completion counted in bytes on the stage's `full` mbarrier) or 8 x cp.async (modes 1 / 2: LDGSTS, 8 lanes
-//     x 16 bytes per row piece, completion by cp.async.mbarrier.arrive.noinc);
-//   * kBgCons CONSUMER warps only read shared memory: a group of 8 lanes (float4 each) owns a row, adds its pieces in stream
-//     order (self first: the same order as the other SpMM kernels), scales and stores it.  Rounds of 4 rows are dealt
-//     round-robin to the warps; control flow is warp-uniform (groups waiting or looping on their own serialised the warp);
-//     a warp releases a stage (one arrival per warp on its `empty` mbarrier) after having seen it full -- that makes an
-//     early arrival for a later use of the slot impossible -- and consumes rounds longer than NS / 4 stages window by
-//     window, so a row may be longer than the whole ring.
+//   * one SCHEDULER warp takes items (32-row blocks: slot, chunk, 128-row tile, quarter -- the numbering of
+//     cspmm_seg_kernel) IN ORDER from the global work counter, loads the block's row ids / list offsets two items ahead
+//     of their use and publishes a descriptor in shared memory: per row the inclusive end of its part of the gather STREAM
+//     (for GCN the row itself first -- the operands are pre-scaled by deg^-1/2, so the unit self loop is one more
+//     unweighted term -- then its active sources in list order), the row id and its first list entry;
+//   * P PRODUCER warps walk the stream 32 positions (= one ring stage) at a time, across item boundaries, with the
+//     source ids of their next stages already loading: lane = position, its row by binary search over the row ends, its
+//     source id from the compacted list; then MODE 0: one bulk copy per lane (UBLKCP), MODE 1 / 2: 8 x cp.async (.cg / .ca,
+//     8 lanes x 16 bytes per row piece), MODE 3: lanes 0 .. 7 issue one gather4 each (4 consecutive positions = 512 bytes
+//     of the stage); completion is counted on the stage's `full` mbarrier (transaction bytes, or
+//     cp.async.mbarrier.arrive.noinc);
+//   * C CONSUMER warps only read shared memory: a group of 8 lanes (float4 each) owns a row, adds its pieces in stream
+//     order, scales and stores it.  Rounds of 4 rows are dealt round-robin to the warps; control flow is warp-uniform
+//     (groups waiting or looping on their own serialised the warp); a warp releases a stage (one arrival per warp on its
+//     `empty` mbarrier) after having seen it full -- that makes an early arrival for a later use of the slot impossible --
+//     and consumes rounds longer than NS / 4 stages window by window, so a row may be longer than the whole ring.
 //
-// Ring: NS stages x 32 slots x 128 bytes (NS = 32: 128 KB per SM).  Rows with more than long_cnt active in-edges are not
-// part of the stream (cspmm_long_kernel sums them, as for the other variants).
+// Ring: NS stages x 32 slots x 128 bytes.  Rows with more than long_cnt active in-edges are not part of the stream
+// (cspmm_long_kernel sums them, as for the other variants).
+#include <cuda.h>
+
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "compact_internal.cuh"
 
@@ -40,17 +48,14 @@ namespace xpgnn {
 
 namespace {
 
-constexpr int kBgProd = 8;   // producer warps
-constexpr int kBgCons = 8;   // consumer warps (16 measured slower: 26.0 vs 20.5 ms)
-constexpr int kBgDesc = 4;   // item descriptors in flight
-constexpr int kBgRows = 128; // rows per item
-constexpr int kBgThreads = 32 * (1 + kBgProd + kBgCons);
+constexpr int kBgDesc = 8;   // item descriptors in flight
+constexpr int kBgRows = 32;  // rows per item
 
 struct BgDesc {
   int aend[kBgRows];     // stream positions of rows 0 .. r (inclusive prefix), relative to the item
   int v[kBgRows];        // node id | -1: no row here / hub row
   uint32_t e[kBgRows];   // first list entry of the row
-  int t, c, len, n_rows; // n_rows < 0: no more items
+  int t, c, len, live;   // live < 0: no more items
   uint32_t stage0;       // global stage index (per CTA) of the item's first stage
   int pad[3];
 };
@@ -114,6 +119,12 @@ __device__ __forceinline__ void bg_bulk_copy(uint32_t smem_dst, const void* gmem
                "r"(bytes), "r"(bg_u32(bar))
                : "memory");
 }
+// TMA gather4: rows r0 .. r3 (columns [0, box width)) of the 2-D tensor map -> 4 consecutive box rows at smem_dst
+__device__ __forceinline__ void bg_gather4(uint32_t smem_dst, const CUtensorMap* tmap, int r0, int r1, int r2, int r3, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(smem_dst),
+               "l"(tmap), "r"(bg_u32(bar)), "r"(0), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+               : "memory");
+}
 __device__ __forceinline__ void bg_add(float4& acc, const float4& x) {  // two packed adds
   asm("{\n\t.reg .b64 a0, a1, x0, x1, one;\n\t"
       "mov.b64 a0, {%0, %1};\n\tmov.b64 a1, {%2, %3};\n\tmov.b64 x0, {%4, %5};\n\tmov.b64 x1, {%6, %7};\n\t"
@@ -124,17 +135,18 @@ __device__ __forceinline__ void bg_add(float4& acc, const float4& x) {  // two p
       : "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w));
 }
 
-// MODE 0: bulk copies (UBLKCP) | 1: cp.async.cg (LDGSTS, 8 lanes x 16 bytes per row piece) | 2: cp.async.ca
-template <int NS, int MODE>  // NS: ring stages, a power of two
-__global__ void __launch_bounds__(kBgThreads, 1) cspmm_bulk_kernel(const CspmmArgs a) {
+// NS: ring stages (a power of two).  MODE 0: bulk copies (UBLKCP) | 1: cp.async.cg | 2: cp.async.ca | 3: TMA gather4.
+// P / C: producer / consumer warps.  MINB: CTAs per SM the register budget is sized for (the hybrid launch shares the SM).
+template <int NS, int MODE, int P, int C, int MINB>
+__global__ void __launch_bounds__(32 * (1 + P + C), MINB) cspmm_bulk_kernel(const CspmmArgs a, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(128) unsigned char bg_raw[];
   BgSmem<NS>& S = *reinterpret_cast<BgSmem<NS>*>(bg_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x <= a.nb) S.start[threadIdx.x] = a.slot_tile_start[threadIdx.x];
   if (threadIdx.x < a.nb) S.nact[threadIdx.x] = a.slot_info[threadIdx.x].x;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NS; ++i) { bg_init(&S.full[i], MODE == 0 ? 1 : 32); bg_init(&S.empty[i], kBgCons); }
-    for (int i = 0; i < kBgDesc; ++i) { bg_init(&S.dfull[i], 1); bg_init(&S.dempty[i], kBgProd + kBgCons); }
+    for (int i = 0; i < NS; ++i) { bg_init(&S.full[i], (MODE == 0 || MODE == 3) ? 1 : 32); bg_init(&S.empty[i], C); }
+    for (int i = 0; i < kBgDesc; ++i) { bg_init(&S.dfull[i], 1); bg_init(&S.dempty[i], P + C); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -144,12 +156,11 @@ __global__ void __launch_bounds__(kBgThreads, 1) cspmm_bulk_kernel(const CspmmAr
   if (warp == 0) {
     // ================= scheduler: items in global order -> descriptors =================
     // Software pipeline: while item n is turned into a descriptor, the metadata loads of n + 1 and n + 2 and the counter
-    // fetch of n + 3 are in flight (under load a DRAM round trip is several microseconds; an item lasts about two).
-    const int total = S.start[a.nb] * a.n_chunks;
+    // fetch of n + 3 are in flight (under load a DRAM round trip is several microseconds).
+    const int total = S.start[a.nb] * a.n_chunks * 4;  // 32-row blocks, ordered slot / chunk / 128-row tile / quarter
     struct Meta {
-      int item, t, c, row0;
-      int v[4];
-      uint32_t e[4], f[4];
+      int item, t, c, v;
+      uint32_t e, f;
     };
     int t_ld = 0;
     auto grab_raw = [&]() {  // lane 0 holds the value; broadcast when it is needed
@@ -159,26 +170,20 @@ __global__ void __launch_bounds__(kBgThreads, 1) cspmm_bulk_kernel(const CspmmAr
     };
     auto load_meta = [&](int item, Meta& m) {
       m.item = item;
-      m.t = 0; m.c = 0; m.row0 = 0;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) { m.v[k] = -1; m.e[k] = 0; m.f[k] = 0; }
+      m.t = 0; m.c = 0; m.v = -1; m.e = 0; m.f = 0;
       if (item >= total) return;
-      while (item >= S.start[t_ld + 1] * a.n_chunks) ++t_ld;
+      const int idx = item >> 2;
+      while (idx >= S.start[t_ld + 1] * a.n_chunks) ++t_ld;
       const int ntb = S.start[t_ld + 1] - S.start[t_ld];
-      const int rem = item - S.start[t_ld] * a.n_chunks;
+      const int rem = idx - S.start[t_ld] * a.n_chunks;
       m.t = t_ld;
       m.c = rem / ntb;
-      m.row0 = (rem - m.c * ntb) * kBgRows;
-      const int n_act = S.nact[t_ld];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int i = m.row0 + k * 32 + lane;
-        if (i < n_act) {
-          m.v[k] = __ldcs(a.act_list + (int64_t)t_ld * a.N + i);
-          const uint32_t* rp = a.rowptr_c + (int64_t)t_ld * (a.N + 1) + i;
-          m.e[k] = __ldcs(rp);
-          m.f[k] = __ldcs(rp + 1);
-        }
+      const int i = (rem - m.c * ntb) * 128 + (item & 3) * 32 + lane;
+      if (i < S.nact[t_ld]) {
+        m.v = __ldcs(a.act_list + (int64_t)t_ld * a.N + i);
+        const uint32_t* rp = a.rowptr_c + (int64_t)t_ld * (a.N + 1) + i;
+        m.e = __ldcs(rp);
+        m.f = __ldcs(rp + 1);
       }
     };
     Meta A, B;
@@ -193,7 +198,7 @@ __global__ void __launch_bounds__(kBgThreads, 1) cspmm_bulk_kernel(const CspmmAr
       BgDesc& D = S.desc[d];
       if (n >= kBgDesc) BG_TIMED(t_w0, bg_wait<64>(&S.dempty[d], ((n / kBgDesc) - 1) & 1));
       if (A.item >= total) {
-        if (lane == 0) D.n_rows = -1;
+        if (lane == 0) D.live = -1;
         __syncwarp();
         if (lane == 0) bg_arrive(&S.dfull[d]);
 #ifdef XPGNN_EXPERIMENTS
@@ -201,37 +206,31 @@ __global__ void __launch_bounds__(kBgThreads, 1) cspmm_bulk_kernel(const CspmmAr
 #endif
         break;
       }
-      int carry = 0;
+      const uint32_t cnt = A.f - A.e;
+      const bool mine = A.v >= 0 && !(a.long_cnt > 0 && cnt > (uint32_t)a.long_cnt);
+      int x = mine ? (int)cnt + gself : 0;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint32_t cnt = A.f[k] - A.e[k];
-        const bool mine = A.v[k] >= 0 && !(a.long_cnt > 0 && cnt > (uint32_t)a.long_cnt);
-        int x = mine ? (int)cnt + gself : 0;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int y = __shfl_up_sync(0xffffffffu, x, o);
-          if (lane >= o) x += y;
-        }
-        D.aend[k * 32 + lane] = carry + x;
-        D.v[k * 32 + lane] = mine ? A.v[k] : -1;
-        D.e[k * 32 + lane] = A.e[k];
-        carry += __shfl_sync(0xffffffffu, x, 31);
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
       }
-      if (lane == 0) {
-        D.t = A.t; D.c = A.c; D.len = carry; D.n_rows = 1; D.stage0 = stage_next;
-      }
-      stage_next += (uint32_t)((carry + 31) >> 5);
+      D.aend[lane] = x;
+      D.v[lane] = mine ? A.v : -1;
+      D.e[lane] = A.e;
+      const int len = __shfl_sync(0xffffffffu, x, 31);
+      if (lane == 0) { D.t = A.t; D.c = A.c; D.len = len; D.live = 1; D.stage0 = stage_next; }
+      stage_next += (uint32_t)((len + 31) >> 5);
       __syncwarp();
       if (lane == 0) bg_arrive(&S.dfull[d]);
       A = B;
       load_meta(__shfl_sync(0xffffffffu, raw, 0), B);
       raw = grab_raw();
     }
-  } else if (warp <= kBgProd) {
+  } else if (warp <= P) {
     // ================= producers: stream positions -> copies into the ring =================
-    // Producer pw owns the stages whose GLOBAL index is pw mod kBgProd.  It walks them as one sequence across item
-    // boundaries with the source ids of the next kBgAhead stages already loading (a FETCH cursor runs ahead of the
-    // ISSUE cursor), so neither a stage nor the first stage of an item waits for a list load.
+    // Producer pw owns the stages whose GLOBAL index is pw mod P.  It walks them as one sequence across item boundaries
+    // with the source ids of the next kAhead stages already loading (a FETCH cursor runs ahead of the ISSUE cursor), so
+    // neither a stage nor the first stage of an item waits for a list load.
     constexpr int kAhead = 3;
     const int pw = warp - 1;
     const int sub = lane & 7, grp = lane >> 3;
@@ -252,9 +251,9 @@ __global__ void __launch_bounds__(kBgThreads, 1) cspmm_bulk_kernel(const CspmmAr
         if (f_nst < 0) {  // open item fn
           if (may_block) BG_TIMED(t_w0, bg_wait<32>(&S.dfull[fn % kBgDesc], (fn / kBgDesc) & 1));
           else if (!bg_test(&S.dfull[fn % kBgDesc], (fn / kBgDesc) & 1)) return 1;
-          if (D.n_rows < 0) { f_end = true; return 2; }
+          if (D.live < 0) { f_end = true; return 2; }
           f_nst = (D.len + 31) >> 5;
-          fk = (int)(((uint32_t)pw + (uint32_t)kBgProd - (D.stage0 % (uint32_t)kBgProd)) % (uint32_t)kBgProd);
+          fk = (int)(((uint32_t)pw + (uint32_t)P - (D.stage0 % (uint32_t)P)) % (uint32_t)P);
         }
         if (fk < f_nst) {
           const int len = D.len, pos = fk * 32 + lane;
@@ -267,7 +266,7 @@ __global__ void __launch_bounds__(kBgThreads, 1) cspmm_bulk_kernel(const CspmmAr
           if (pos < len) {
             int r = 0;  // rows whose stream ends at or before pos
 #pragma unroll
-            for (int step = 64; step >= 1; step >>= 1)
+            for (int step = kBgRows / 2; step >= 1; step >>= 1)
               if (D.aend[r + step - 1] <= pos) r += step;
             const int ar = r ? D.aend[r - 1] : 0;
             if (gcn && pos == ar) id = D.v[r];
@@ -275,7 +274,7 @@ __global__ void __launch_bounds__(kBgThreads, 1) cspmm_bulk_kernel(const CspmmAr
           }
           g = D.stage0 + (uint32_t)fk;
           item_no = fn;
-          fk += kBgProd;
+          fk += P;
           return 0;
         }
         ++fn;
@@ -295,33 +294,51 @@ __global__ void __launch_bounds__(kBgThreads, 1) cspmm_bulk_kernel(const CspmmAr
       const BgDesc& D = S.desc[item_no % kBgDesc];
       const uint32_t slot = g % NS, use = g / NS;
       const int k = (int)(g - D.stage0);
-      const char* in_c = reinterpret_cast<const char*>(a.in + (int64_t)D.t * a.in_s_stride + (int64_t)D.c * a.in_chunk_stride);
+      const int n_valid = min(32, D.len - k * 32);
       if (use > 0) BG_TIMED(t_w1, bg_wait<64>(&S.empty[slot], (use - 1) & 1));
       ++n_st;
-      if (MODE == 0) {
-        if (lane == 0) bg_arrive_expect_tx(&S.full[slot], (uint32_t)min(32, D.len - k * 32) * 128u);
-        __syncwarp();
-        if (id >= 0) {
-          const char* src;
-          asm("mad.wide.u32 %0, %1, 128, %2;" : "=l"(src) : "r"((uint32_t)id), "l"(in_c));
-          bg_bulk_copy(bg_u32(&S.ring[slot][lane][0]), src, 128u, &S.full[slot]);
-        }
-      } else {
-        const uint32_t dst0 = bg_u32(&S.ring[slot][0][0]) + (uint32_t)sub * 16u;
-        const char* in_l = in_c + sub * 16;
+      if (MODE == 3) {
+        // rows of the 2-D view [all slots x chunks x nodes][32 floats] of the operand buffer: row = (t, c) base + node
+        const int row_base = (int)(((int64_t)D.t * a.in_s_stride + (int64_t)D.c * a.in_chunk_stride) >> 5);
+        const int n_g4 = (n_valid + 3) >> 2;
+        if (lane == 0) bg_arrive_expect_tx(&S.full[slot], (uint32_t)n_g4 * 512u);
+        // positions past the end of the stream are padded with the first id of the stage (loaded, never summed)
+        const int id0 = __shfl_sync(0xffffffffu, id, 0);
+        int r4[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int pj = j * 4 + grp;  // slot of the stage: 8 lanes x 16 bytes each
-          const int idj = __shfl_sync(0xffffffffu, id, pj);
-          if (idj >= 0) {
-            const char* src;
-            asm("mad.wide.u32 %0, %1, 128, %2;" : "=l"(src) : "r"((uint32_t)idj), "l"(in_l));
-            if (MODE == 1) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + (uint32_t)pj * 128u), "l"(src) : "memory");
-            else asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst0 + (uint32_t)pj * 128u), "l"(src) : "memory");
-          }
+        for (int j = 0; j < 4; ++j) {
+          const int idj = __shfl_sync(0xffffffffu, id, (4 * lane + j) & 31);
+          r4[j] = row_base + (idj >= 0 ? idj : id0);
         }
-        // the stage is full once every producer lane's copies have landed (32 arrivals, none added by the instruction)
-        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bg_u32(&S.full[slot])) : "memory");
+        __syncwarp();
+        if (lane < n_g4) bg_gather4(bg_u32(&S.ring[slot][(4 * lane) & 31][0]), &tmap, r4[0], r4[1], r4[2], r4[3], &S.full[slot]);
+      } else {
+        const char* in_c = reinterpret_cast<const char*>(a.in + (int64_t)D.t * a.in_s_stride + (int64_t)D.c * a.in_chunk_stride);
+        if (MODE == 0) {
+          if (lane == 0) bg_arrive_expect_tx(&S.full[slot], (uint32_t)n_valid * 128u);
+          __syncwarp();
+          if (id >= 0) {
+            const char* src;
+            asm("mad.wide.u32 %0, %1, 128, %2;" : "=l"(src) : "r"((uint32_t)id), "l"(in_c));
+            bg_bulk_copy(bg_u32(&S.ring[slot][lane][0]), src, 128u, &S.full[slot]);
+          }
+        } else {
+          const uint32_t dst0 = bg_u32(&S.ring[slot][0][0]) + (uint32_t)sub * 16u;
+          const char* in_l = in_c + sub * 16;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int pj = j * 4 + grp;  // slot of the stage: 8 lanes x 16 bytes each
+            const int idj = __shfl_sync(0xffffffffu, id, pj);
+            if (idj >= 0) {
+              const char* src;
+              asm("mad.wide.u32 %0, %1, 128, %2;" : "=l"(src) : "r"((uint32_t)idj), "l"(in_l));
+              if (MODE == 1) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + (uint32_t)pj * 128u), "l"(src) : "memory");
+              else asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst0 + (uint32_t)pj * 128u), "l"(src) : "memory");
+            }
+          }
+          // the stage is full once every producer lane's copies have landed (32 arrivals, none added by the instruction)
+          asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bg_u32(&S.full[slot])) : "memory");
+        }
       }
     };
     // The queue is a FIFO over kAhead register slots used round-robin (the loop is unrolled, so slot indices are compile-time
@@ -382,13 +399,12 @@ __global__ void __launch_bounds__(kBgThreads, 1) cspmm_bulk_kernel(const CspmmAr
   } else {
     // ================= consumers: a group of 8 lanes sums a row from the ring =================
     // Round k of an item = rows 4k .. 4k + 3 (one per group), dealt round-robin to the consumer warps, so all warps work
-    // next to the fill front.  Releases are per WARP (kBgCons arrivals per stage): before a round the warp releases every
-    // stage below the round's first one -- lanes take different stages; each stage is seen full first, which makes an early
-    // arrival for a later use of the slot impossible -- and a round longer than kWin stages is consumed window by window, so
-    // no row length can hold more than kWin + 1 stages unreleased (a row may be longer than the whole ring).
+    // next to the fill front.  Releases are per WARP (C arrivals per stage): before a round the warp releases every stage
+    // below the round's first one -- lanes take different stages; each stage is seen full first -- and a round longer than
+    // kWin stages is consumed window by window, so no row length can hold more than kWin + 1 stages unreleased.
     constexpr int kWin = NS / 4;
     constexpr int kPar = NS < 32 ? NS : 32;
-    const int cw = warp - 1 - kBgProd, sub = lane & 7, grp = lane >> 3;
+    const int cw = warp - 1 - P, sub = lane & 7, grp = lane >> 3;
     uint32_t rel = 0;   // every stage below `rel` has been released by this warp (warp-uniform)
     unsigned long long t_w0 = 0, t_w1 = 0, t_w2 = 0, n_rd = 0;
     const long long t_begin = clock64();
@@ -406,11 +422,11 @@ __global__ void __launch_bounds__(kBgThreads, 1) cspmm_bulk_kernel(const CspmmAr
       const int d = n % kBgDesc;
       const BgDesc& D = S.desc[d];
       BG_TIMED(t_w0, bg_wait<32>(&S.dfull[d], (n / kBgDesc) & 1));
-      if (D.n_rows < 0) break;
+      if (D.live < 0) break;
       const uint32_t stage0 = D.stage0;
       const int nst = (D.len + 31) >> 5;
       float* out_c = a.out + (int64_t)D.t * a.out_s_stride + (int64_t)D.c * a.out_chunk_stride + sub * 4;
-      for (int k = cw; k < kBgRows / 4; k += kBgCons) {
+      for (int k = cw; k < kBgRows / 4; k += C) {
         const int P0 = k ? D.aend[4 * k - 1] : 0, P1 = D.aend[4 * k + 3];
         if (P1 == P0 && D.v[4 * k] < 0 && D.v[4 * k + 1] < 0 && D.v[4 * k + 2] < 0 && D.v[4 * k + 3] < 0) continue;  // no rows here
         const int r = 4 * k + grp;
@@ -420,8 +436,6 @@ __global__ void __launch_bounds__(kBgThreads, 1) cspmm_bulk_kernel(const CspmmAr
         const int sa = P0 >> 5, sb = (P1 + 31) >> 5;  // the round's positions sit in stages [sa, sb) of the item
         BG_TIMED(t_w1, release_to(stage0 + (uint32_t)sa));
         ++n_rd;
-        // Warp-uniform control flow (groups that wait or loop on their own serialise the warp: 2900 cycles per round
-        // measured): every lane waits for every stage of the window, then all groups run the same number of predicated steps.
         for (int ws = sa; ws < sb; ws += kWin) {
           const int we = min(ws + kWin, sb);
           for (int gg = ws; gg < we; ++gg) {
@@ -464,23 +478,43 @@ __global__ void __launch_bounds__(kBgThreads, 1) cspmm_bulk_kernel(const CspmmAr
   }
 }
 
-}  // namespace
+// 2-D tensor map over the chunk-major operand buffer seen as [rows][32 floats] (box = one 128-byte row: the gather4 form
+// loads four of them per instruction).  Encoding goes through the driver entry point (no link dependency on libcuda).
+typedef CUresult (*BgEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int bg_tensor_map(const float* base, uint64_t rows, CUtensorMap* out) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, uint64_t>, CUtensorMap> cache;
+  static BgEncodeFn encode = nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find({base, rows});
+  if (it != cache.end()) { *out = it->second; return 0; }
+  if (!encode) {
+    cudaDriverEntryPointQueryResult qres;
+    XP_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void**)&encode, cudaEnableDefault, &qres));
+    XP_REQUIRE(encode != nullptr, "cuTensorMapEncodeTiled is not available");
+  }
+  CUtensorMap m;
+  memset(&m, 0, sizeof m);
+  const cuuint64_t dims[2] = {32, rows};
+  const cuuint64_t strides[1] = {128};
+  const cuuint32_t box[2] = {32, 1};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  XP_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed");
+  if (cache.size() > 64) cache.clear();
+  cache[{base, rows}] = m;
+  *out = m;
+  return 0;
+}
 
-int launch_cspmm_bulk(const CspmmArgs& a, int variant, cudaStream_t st) {
-  // variant = 100 * mode + ring stages: mode 0 bulk copies | 1 cp.async.cg | 2 cp.async.ca; stages 16 | 32
-  const int mode = variant / 100, ns = variant % 100;
-  void (*k)(const CspmmArgs);
-  int smem;
-#define BG_PICK(NS_)                                                                                          \
-  do {                                                                                                        \
-    k = mode == 0 ? cspmm_bulk_kernel<NS_, 0> : (mode == 1 ? cspmm_bulk_kernel<NS_, 1> : cspmm_bulk_kernel<NS_, 2>); \
-    smem = (int)sizeof(BgSmem<NS_>);                                                                          \
-  } while (0)
-  if (ns >= 32) BG_PICK(32);
-  else BG_PICK(16);
-#undef BG_PICK
+template <int NS, int MODE, int P, int C, int MINB>
+int bg_launch(const CspmmArgs& a, const CUtensorMap& tmap, cudaStream_t st, int variant) {
+  void (*k)(const CspmmArgs, const CUtensorMap) = cspmm_bulk_kernel<NS, MODE, P, C, MINB>;
+  const int smem = (int)sizeof(BgSmem<NS>);
   XP_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  XP_LAUNCH(k, kNumSMs, kBgThreads, smem, st, a);
+  XP_LAUNCH(k, kNumSMs, 32 * (1 + P + C), smem, st, a, tmap);
 #ifdef XPGNN_EXPERIMENTS
   static const bool dbg_on = getenv("XPGNN_BG_DBG") != nullptr;
   static int n_launch = 0;
@@ -494,7 +528,35 @@ int launch_cspmm_bulk(const CspmmArgs& a, int variant, cudaStream_t st) {
             variant, h[0], h[1], h[2], h[4], h[5], h[6], h[7], h[8], h[10], h[11], h[12], h[13], h[14]);
   }
 #endif
+  (void)variant;
   return 0;
+}
+
+}  // namespace
+
+int launch_cspmm_bulk(const CspmmArgs& a, int variant, cudaStream_t st) {
+  // variant = 100 * mode + ring stages (16 | 32); mode 0 bulk copies | 1 cp.async.cg | 2 cp.async.ca | 3 TMA gather4 |
+  // 4 TMA gather4, the small configuration that runs next to cspmm_seg_kernel (2 producer + 4 consumer warps, 16 stages)
+  const int mode = variant / 100, ns = variant % 100;
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof tmap);
+  if (mode >= 3) {
+    XP_REQUIRE(a.in_s_stride % 32 == 0 && a.in_chunk_stride % 32 == 0, "gather4: operand strides must be whole 128-byte rows");
+    const uint64_t rows = (uint64_t)((int64_t)(a.nb - 1) * a.in_s_stride + (int64_t)(a.n_chunks - 1) * a.in_chunk_stride) / 32 + (uint64_t)a.N;
+    XP_REQUIRE(rows < (1ull << 31), "gather4: row index does not fit 31 bits");
+    if (bg_tensor_map(a.in, rows, &tmap)) return 1;
+  }
+  if (mode == 4) return bg_launch<16, 3, 2, 4, 2>(a, tmap, st, variant);
+  if (ns >= 32) {
+    if (mode == 0) return bg_launch<32, 0, 8, 8, 1>(a, tmap, st, variant);
+    if (mode == 1) return bg_launch<32, 1, 8, 8, 1>(a, tmap, st, variant);
+    if (mode == 2) return bg_launch<32, 2, 8, 8, 1>(a, tmap, st, variant);
+    return bg_launch<32, 3, 4, 8, 1>(a, tmap, st, variant);
+  }
+  if (mode == 0) return bg_launch<16, 0, 8, 8, 1>(a, tmap, st, variant);
+  if (mode == 1) return bg_launch<16, 1, 8, 8, 1>(a, tmap, st, variant);
+  if (mode == 2) return bg_launch<16, 2, 8, 8, 1>(a, tmap, st, variant);
+  return bg_launch<16, 3, 4, 8, 1>(a, tmap, st, variant);
 }
 
 }  // namespace xpgnn

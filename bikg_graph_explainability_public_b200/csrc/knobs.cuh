@@ -16,6 +16,8 @@ struct Knobs {
   int seg = 8;             // XPGNN_SEG: 0 row-lockstep SpMM | 4 / 6 / 8 segmented SpMM with that many gathers in flight per lane
                            // (measured at C3: 8 at 6 CTAs / SM 11.07 ms per tile, 6 at 6: 11.41, 4 at 8: 13.64, row-lockstep 11.59)
   int seg_occ = 0;         // XPGNN_SEG_OCC: 0 default CTAs / SM of the chosen segmented variant
+  int seg_tma = 0;         // XPGNN_SEG_TMA: 1 = a small TMA gather4 kernel (compact_bulk.cu) runs next to the segmented SpMM on a second stream;
+                           // both take blocks from the same in-order counter (bit-identical results)
   int l2_stream = 1;       // XPGNN_L2_STREAM / XPGNN_L2_GATHER: L2 eviction priority of streamed / gathered accesses
   int l2_gather = 0;
   int sched_static = 0;    // XPGNN_SCHED=static: static round-robin instead of the in-order work counter
