@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(256) compact_finalize_kernel(const unsigned lo
                                                                float* __restrict__ wgt, int2* __restrict__ slot_info,
                                                                long long* __restrict__ slot_base, int32_t* __restrict__ rows_packed,
                                                                float* __restrict__ rs_packed, int long_cnt, int32_t* __restrict__ long_list,
-                                                               int32_t* __restrict__ n_long_list) {
+                                                               int32_t* __restrict__ n_long_list, int long_cap) {
   const int t = blockIdx.y;
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   // first 128-row tile of this slot in the concatenated, per-slot padded tile table
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256) compact_finalize_kernel(const unsigned lo
     rows_packed[(int64_t)s_tile0 * 128 + i] = (int32_t)(((uint32_t)t << kPackShift) | (uint32_t)(row_lo + v));
     rs_packed[(int64_t)s_tile0 * 128 + i] = gcn_dinv((uint32_t)(K & kEdgeMask));
     if (long_cnt > 0 && (K & kEdgeMask) > (unsigned long long)long_cnt)  // hub row of this coalition: cspmm_long_kernel
-      long_list[atomicAdd(n_long_list, 1)] = (int32_t)(((uint32_t)t << kPackShift) | (uint32_t)i);
+      long_list[(int64_t)t * long_cap + atomicAdd(n_long_list + t, 1)] = i;  // per-slot segment: the long-row kernel works pass by pass
   }
   if (wgt) wgt[g] = gcn_dinv((uint32_t)(K & kEdgeMask));
   if (v == N - 1) {
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(256) compact_tilemap_kernel(const int2* __rest
                                                               int32_t* __restrict__ n_tiles, int n_layers,
                                                               int64_t* stats, int32_t* __restrict__ counters, int count_tile) {
   __shared__ int start[33];
-  if (threadIdx.x < 16) counters[threadIdx.x] = 0;  // work counters of the SpMM launches of this tile
+  if (threadIdx.x < 32) counters[threadIdx.x] = 0;  // work counters of the SpMM launches of this tile (16 + l: long-row kernel of layer l)
   if (threadIdx.x == 0) {
     int acc = 0;
     long long active = 0;
@@ -411,16 +411,40 @@ __global__ void __launch_bounds__(256, OCC) cspmm_kernel(const CspmmArgs a) {
 
 // Long compact rows (hub rows of power-law graphs): one CTA per (row, chunk).  The 32 row groups of the CTA take
 // contiguous slices of the row's active in-edges; the partial sums are added in a fixed order through shared memory.
+// Items are ordered slot / chunk / row (the long rows of a slot sit in their own segment of the list) and handed out in
+// that order by a work counter, so the whole grid gathers from ONE (slot, chunk) operand at a time, like the main kernel
+// (r02 launch list of the R-MAT C3 step: with the items in list order -- 4 chunks of a row next to each other, slots mixed --
+// this kernel took 5.8 ms per tile for a third of the active edges).  The source ids of the next batch load while the current
+// batch gathers.
 template <int CW, bool WEIGHTED>
 __global__ void __launch_bounds__(256) cspmm_long_kernel(const CspmmArgs a) {
   constexpr int G = CW / 4, NG = 256 / G;
   __shared__ float4 s_red[256];
+  __shared__ int s_off[33];  // first item of every slot: items = rows x chunks
+  __shared__ int s_item;
   const int lane = threadIdx.x & 31, sub = threadIdx.x % G, g = threadIdx.x / G, grp = lane / G;
   const uint64_t pol_s = l2_policy(a.l2_stream), pol_g = l2_policy(a.l2_gather);
-  const int total = *a.n_long_list * a.n_chunks;
-  for (int idx = blockIdx.x; idx < total; idx += gridDim.x) {
-    const int32_t ent = a.long_list[idx / a.n_chunks];
-    const int c = idx % a.n_chunks, t = (int)((uint32_t)ent >> kPackShift), i = ent & ((1 << kPackShift) - 1);
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int t = 0; t < a.nb; ++t) { s_off[t] = acc; acc += a.n_long_list[t] * a.n_chunks; }
+    s_off[a.nb] = acc;
+  }
+  __syncthreads();
+  const int total = s_off[a.nb];
+  int t = 0;
+  int idx = blockIdx.x;
+  while (true) {
+    if (a.counter_long) {
+      __syncthreads();  // everybody has read the previous item (and, the first time, s_off)
+      if (threadIdx.x == 0) s_item = atomicAdd(a.counter_long, 1);
+      __syncthreads();
+      idx = s_item;
+    }
+    if (idx >= total) break;
+    while (idx >= s_off[t + 1]) ++t;
+    const int n_t = a.n_long_list[t];
+    const int rem = idx - s_off[t];
+    const int c = rem / n_t, i = a.long_list[(int64_t)t * a.long_cap + (rem - c * n_t)];
     const uint32_t* rp = a.rowptr_c + (int64_t)t * (a.N + 1);
     const int v = a.act_list[(int64_t)t * a.N + i];
     const uint32_t e0 = rp[i], cnt = rp[i + 1] - e0;
@@ -435,17 +459,25 @@ __global__ void __launch_bounds__(256) cspmm_long_kernel(const CspmmArgs a) {
     const uint32_t bs = (uint32_t)(((uint64_t)g * nbt) / NG) * G, be = min(cnt, (uint32_t)(((uint64_t)(g + 1) * nbt) / NG) * G);
     const uint32_t span = __reduce_max_sync(0xffffffffu, be > bs ? be - bs : 0u);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int my = -1;
+    float myw = 0.f;
+    if (bs + sub < be) {
+      my = ld_hint(cc + bs + sub, pol_s);
+      if (WEIGHTED) myw = __ldg(wg + my);
+    }
     for (uint32_t off = 0; off < span; off += G) {
-      int my = -1;
-      float myw = 0.f;
-      if (bs + off + sub < be) {
-        my = ld_hint(cc + bs + off + sub, pol_s);
+      const int cur = my;
+      const float curw = myw;
+      my = -1;
+      myw = 0.f;
+      if (off + G < span && bs + off + G + sub < be) {  // next batch's ids fly while this batch gathers
+        my = ld_hint(cc + bs + off + G + sub, pol_s);
         if (WEIGHTED) myw = __ldg(wg + my);
       }
 #pragma unroll
       for (int j = 0; j < G; ++j) {
-        const int u = __shfl_sync(0xffffffffu, my, grp * G + j);
-        const float wj = WEIGHTED ? __shfl_sync(0xffffffffu, myw, grp * G + j) : 1.0f;
+        const int u = __shfl_sync(0xffffffffu, cur, grp * G + j);
+        const float wj = WEIGHTED ? __shfl_sync(0xffffffffu, curw, grp * G + j) : 1.0f;
         if (u >= 0) {
           const float4 x = ld_hint4(in_c + (int64_t)u * CW, pol_g);
           acc.x = fmaf(wj, x.x, acc.x); acc.y = fmaf(wj, x.y, acc.y);
@@ -463,6 +495,7 @@ __global__ void __launch_bounds__(256) cspmm_long_kernel(const CspmmArgs a) {
       }
       cspmm_epilogue<CW>(a, cnt, acc, in_c, out_c, add_c, bias, v, pol_s, pol_g);
     }
+    if (!a.counter_long) idx += gridDim.x;
   }
 }
 
@@ -1303,6 +1336,7 @@ struct CLayout {
   int32_t *slot_tile_start, *n_tiles, *counters;
   int32_t *long_rows, *n_long;
   int32_t *long_list, *n_long_list;
+  int long_cap;  // entries per slot segment of long_list
   int32_t* rows_packed;
   float* rs_packed;
   int32_t* ccol;
@@ -1334,11 +1368,12 @@ static CLayout compact_carve(const xpgnn_plan_t* p, void* ws, int64_t cap, int t
   c.slot_base = b.take<long long>(32);
   c.slot_tile_start = b.take<int32_t>(33);
   c.n_tiles = b.take<int32_t>(1);
-  c.counters = b.take<int32_t>(16);
+  c.counters = b.take<int32_t>(32);
   c.long_rows = b.take<int32_t>(E / kLongRow + 1);
   c.n_long = b.take<int32_t>(1);
-  c.long_list = b.take<int32_t>((int64_t)tile * (E / kLongCompact + 1));
-  c.n_long_list = b.take<int32_t>(1);
+  c.long_cap = (int)(E / kLongCompact + 1);
+  c.long_list = b.take<int32_t>((int64_t)tile * c.long_cap);
+  c.n_long_list = b.take<int32_t>(32);
   c.rows_packed = b.take<int32_t>((int64_t)tile * ceil_div(N, 128) * 128);
   c.rs_packed = b.take<float>((int64_t)tile * ceil_div(N, 128) * 128);
   c.ccol = b.take<int32_t>((int64_t)tile * E);
@@ -1358,7 +1393,8 @@ static int launch_cspmm(const CspmmArgs& a, int cw, cudaStream_t st) {
   const int occ = knobs().occ;
   void (*k)(const CspmmArgs);
   // aggregate-first layers >= 1 (plain scaled sums over 32-float chunks): the segmented kernel
-  const int seg = knobs().seg;  // 0: row-lockstep kernel | 4 / 6 / 8: gathers in flight per lane
+  int seg = knobs().seg;  // 0: row-lockstep kernel | 4 / 6 / 8: gathers in flight per lane
+  if (seg == 8 && a.long_cnt > 0 && knobs().seg_skew > 0) seg = knobs().seg_skew;  // hub rows in the graph: skewed degrees
   if (seg > 0 && cw == 32 && a.counter && !a.wgt && !a.addend && !a.bias && !a.layer0 && !a.prescale && a.act_fn == XPGNN_ACT_NONE) {
     const int socc = knobs().seg_occ;
     if (seg >= 200) {  // warp-specialised TMA bulk-copy variant (compact_bulk.cu): seg = 200 + 100 * mode + ring stages (16 | 32): 216 / 232 bulk copies, 316 / 332 cp.async.cg, 432 cp.async.ca, 516 / 532 TMA gather4
@@ -1500,13 +1536,13 @@ int forward_compact(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32
       {
         ProfScope ps(PROF_COMPACT, st);
         if (nb < tile) XP_CHECK(cudaMemsetAsync(lay.keys + (int64_t)nb * N, 0, sizeof(unsigned long long), st));
-        XP_CHECK(cudaMemsetAsync(lay.n_long_list, 0, sizeof(int32_t), st));
+        XP_CHECK(cudaMemsetAsync(lay.n_long_list, 0, 32 * sizeof(int32_t), st));
         size_t tmp = lay.cub_bytes;
         XP_CHECK(cub::DeviceScan::ExclusiveSum(lay.cub_tmp, tmp, lay.keys, lay.scanned, (int64_t)nb * N + 1, st));
         g_launches.fetch_add(1, std::memory_order_relaxed);
         XP_LAUNCH(compact_finalize_kernel, dim3((unsigned)ceil_div(N, 256), (unsigned)nb), 256, 0, st, lay.keys, lay.scanned, N, 0,
                   lay.act_list, lay.rowptr_c, (kind == XPGNN_CONV_GCN && !l0_rows) ? lay.wgt : nullptr, lay.slot_info, lay.slot_base,
-                  lay.rows_packed, lay.rs_packed, n_long > 0 ? kLongCompact : 0, lay.long_list, lay.n_long_list);
+                  lay.rows_packed, lay.rs_packed, n_long > 0 ? kLongCompact : 0, lay.long_list, lay.n_long_list, lay.long_cap);
         XP_LAUNCH(compact_tilemap_kernel, 1, 256, 0, st, lay.slot_info, nb, lay.slot_tile_start, lay.n_tiles, NL, stats, lay.counters, 1);
         XP_LAUNCH(compact_edges_kernel, grid_rows, 256, 0, st, R0.rowptr, R0.col, lay.ebits, act, W, w, b0, nb, N, lay.scanned, lay.ccol,
                   lay.counters + 14, n_long > 0 ? kLongRow : 0, 0);
@@ -1528,6 +1564,7 @@ int forward_compact(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32
         s.counter = dyn_sched ? lay.counters + l : nullptr;
         s.l2_stream = l2_stream; s.l2_gather = l2_gather;
         s.long_cnt = n_long > 0 ? kLongCompact : 0; s.long_list = lay.long_list; s.n_long_list = lay.n_long_list;
+        s.long_cap = lay.long_cap; s.counter_long = dyn_sched ? lay.counters + 16 + std::min(l, 12) : nullptr;
         if (l == 0 && l0_rows) {
           L0RowsArgs r{};
           r.rowptr = R.rowptr; r.col = R.col; r.ebits = lay.ebits; r.act = act; r.W = W; r.w = w; r.b0 = b0; r.nb = nb; r.N = N;
@@ -1707,6 +1744,7 @@ struct HCsr {  // one unique relation CSR and its per-tile compaction
   uint32_t* ebits;
   float *scale, *wgt, *rs_packed;
   int32_t *act_list, *slot_tile_start, *n_tiles, *counters, *long_rows, *n_long_dev, *long_list, *n_long_list, *rows_packed, *ccol;
+  int long_cap;
   uint32_t* rowptr_c;
   int2* slot_info;
   long long* slot_base;
@@ -1806,11 +1844,12 @@ static HLayout hetero_carve(const xpgnn_plan_t* p, void* ws, int64_t cap, int ti
     c.slot_base = b.take<long long>(32);
     c.slot_tile_start = b.take<int32_t>(33);
     c.n_tiles = b.take<int32_t>(1);
-    c.counters = b.take<int32_t>(16);
+    c.counters = b.take<int32_t>(32);
     c.long_rows = b.take<int32_t>(E / kLongRow + 1);
     c.n_long_dev = b.take<int32_t>(1);
-    c.long_list = b.take<int32_t>((int64_t)tile * (E / kLongCompact + 1));
-    c.n_long_list = b.take<int32_t>(1);
+    c.long_cap = (int)(E / kLongCompact + 1);
+  c.long_list = b.take<int32_t>((int64_t)tile * c.long_cap);
+    c.n_long_list = b.take<int32_t>(32);
     c.rows_packed = b.take<int32_t>((int64_t)tile * ceil_div(nd, 128) * 128);
     c.rs_packed = b.take<float>((int64_t)tile * ceil_div(nd, 128) * 128);
     c.ccol = b.take<int32_t>((int64_t)tile * E);
@@ -1976,13 +2015,13 @@ int forward_compact_hetero(const xpgnn_plan_t* p, const uint32_t* act, int32_t W
         }
         ProfScope ps(PROF_COMPACT, st);
         XP_CHECK(cudaMemsetAsync(lay.keys + (int64_t)nb * nd, 0, sizeof(unsigned long long), st));  // sentinel of the scan
-        XP_CHECK(cudaMemsetAsync(c.n_long_list, 0, sizeof(int32_t), st));
+        XP_CHECK(cudaMemsetAsync(c.n_long_list, 0, 32 * sizeof(int32_t), st));
         size_t tmp = lay.cub_bytes;
         XP_CHECK(cub::DeviceScan::ExclusiveSum(lay.cub_tmp, tmp, lay.keys, lay.scanned, (int64_t)nb * nd + 1, st));
         g_launches.fetch_add(1, std::memory_order_relaxed);
         XP_LAUNCH(compact_finalize_kernel, dim3((unsigned)ceil_div(nd, 256), (unsigned)nb), 256, 0, st, lay.keys, lay.scanned, nd, c.lo,
                   c.act_list, c.rowptr_c, c.wgt, c.slot_info, c.slot_base, c.rows_packed, c.rs_packed, lt ? kLongCompact : 0,
-                  c.long_list, c.n_long_list);
+                  c.long_list, c.n_long_list, c.long_cap);
         XP_LAUNCH(compact_tilemap_kernel, 1, 256, 0, st, c.slot_info, nb, c.slot_tile_start, c.n_tiles, c.n_layers_using, stats,
                   c.counters, i == 0 ? 1 : 0);
         XP_LAUNCH(compact_edges_kernel, grid_nd, 256, 0, st, c.rowptr, c.col, c.ebits, act, W, w, b0, nb, nd, lay.scanned, c.ccol,
@@ -2122,6 +2161,7 @@ int forward_compact_hetero(const xpgnn_plan_t* p, const uint32_t* act, int32_t W
             s.out = lay.agg; s.out_s_stride = hstride; s.out_chunk_stride = cstride; s.act_fn = XPGNN_ACT_NONE;
             s.counter = c.counters + std::min(l, 12); s.l2_stream = 1; s.l2_gather = 0;
             s.long_cnt = c.n_long > 0 ? kLongCompact : 0; s.long_list = c.long_list; s.n_long_list = c.n_long_list;
+            s.long_cap = c.long_cap; s.counter_long = c.counters + 16 + std::min(l, 12);
             if (launch_cspmm(s, cw, st)) return 1;
             const bool root = last[l][r] && group_root[l][r];
             DenseArgs d{};

@@ -97,8 +97,10 @@ struct CspmmArgs {
   const float* bias;          // per-column addend or NULL
   int32_t* counter;           // work counter (zeroed per launch); NULL: static round-robin
   int long_cnt;               // compact rows with more active in-edges are left to cspmm_long_kernel (0: none)
-  const int32_t* long_list;   // entries slot << 26 | compact row, written by compact_finalize_kernel
-  const int32_t* n_long_list;
+  const int32_t* long_list;   // [nb][long_cap] compact rows of the slot, written by compact_finalize_kernel
+  const int32_t* n_long_list; // [nb]
+  int long_cap;
+  int32_t* counter_long;      // work counter of cspmm_long_kernel (zeroed per tile); NULL: static round-robin
   int l2_stream, l2_gather;   // eviction priority of the streamed / gathered accesses (l2_policy kinds)
   float* out;
   int64_t out_s_stride, out_chunk_stride;
