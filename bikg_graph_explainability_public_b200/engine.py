@@ -143,7 +143,10 @@ class MaskedForward:
         p.n_query, p.query, p.out_col = int(q.numel()), q.data_ptr(), int(out_col)
         p.prune, p.hop = int(bool(prune)), _lib.dptr(hop_t)
         p.zero_edge_rule = int(bool(zero_edge_rule))
-        p.precision = {"fp32": 0, "bf16": 1, "bf16_act": 2}[precision]
+        # "fp32": fp32 storage, dense transforms as 3xTF32 tcgen05 products (~1e-6 relative); "fp32_exact": the same plan with
+        # exact fp32 FMA transforms (the dense_simt engine option, set around every call of this engine)
+        p.precision = {"fp32": 0, "fp32_exact": 0, "bf16": 1, "bf16_act": 2}[precision]
+        self.exact_transforms = precision == "fp32_exact"
         self.plan, self.n_query, self.device = p, int(q.numel()), dev
         self.stats = torch.zeros(4, dtype=torch.int64, device=dev)
         # workspace: the largest coalition tile that fits
@@ -187,7 +190,12 @@ class MaskedForward:
         assert act.is_cuda and act.dim() == 2 and act.shape[0] == self.graph.n_nodes and act.is_contiguous()
         w = int(act.shape[1])
         y = torch.empty((n_s, self.n_query), dtype=torch.float32, device=self.device)
-        _lib.check(self.lib.xpgnn_forward(C.byref(self.plan), act.data_ptr(), w, int(s0), int(n_s), y.data_ptr(),
-                                          self.workspace.data_ptr(), int(self.workspace.numel()),
-                                          self.stats.data_ptr(), _lib.stream_ptr()))
+        old = _lib.set_options(dense_simt=1) if self.exact_transforms else None
+        try:
+            _lib.check(self.lib.xpgnn_forward(C.byref(self.plan), act.data_ptr(), w, int(s0), int(n_s), y.data_ptr(),
+                                              self.workspace.data_ptr(), int(self.workspace.numel()),
+                                              self.stats.data_ptr(), _lib.stream_ptr()))
+        finally:
+            if old is not None:
+                _lib.set_options(**old)
         return y

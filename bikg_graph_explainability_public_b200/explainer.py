@@ -208,7 +208,8 @@ def check_ranks_agree(act):
 
 class Explainer:
     #: engine knobs (extension).  precision "fp32": fp32 storage and accumulation, dense transforms as 3xTF32 tensor-core
-    #: products (error ~1e-6 relative, inside the 1e-4 bar); "bf16" / "bf16_act": the 2e-2 bar.  verify: compare the
+    #: products (error ~1e-6 relative, inside the 1e-4 bar); "fp32_exact": exact fp32 FMA transforms (slower, for audits);
+    #: "bf16" / "bf16_act": the 2e-2 bar.  verify: compare the
     #: lowered plan with ``arch`` itself on a probe graph before explaining (see ``verify_lowering``).
     engine_options = dict(prune=True, precision="fp32", verify=True)
 

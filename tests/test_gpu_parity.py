@@ -586,6 +586,30 @@ def test_bf16_activation_storage_within_tolerance(lib):
     np.testing.assert_allclose(y8, y, rtol=1e-6, atol=1e-7)
 
 
+def test_fp32_exact_transforms_option(lib):
+    """precision="fp32_exact": the dense transforms run as exact fp32 FMAs (not 3xTF32 tensor-core products): tighter
+    against the oracle than the 1e-4 bar needs, and the engine option it sets is restored after every call."""
+    import ctypes as C
+
+    from bikg_graph_explainability_public_b200 import _lib
+    from bikg_graph_explainability_public_b200.engine import GraphSpec, MaskedForward
+    from bikg_graph_explainability_public_b200.lowering import lower
+    from oracle.xpgnn_oracle import kernel_output
+
+    x, ei, arch, mask, q = _random_model_case(9, "gcn", n=3000, e=30000, f=64, hidden=(128, 128), s=40)
+    s, n = mask.shape
+    _, y_ref = kernel_output(mask.numpy(), x, ei.numpy(), arch, q)
+    act = _pack(lib, mask)
+    g = GraphSpec(x.cuda(), ei.cuda(), [0, n])
+    y = MaskedForward(g, lower(arch), [q], precision="fp32_exact")(act, s)[:, 0].cpu().numpy()
+    np.testing.assert_allclose(y, y_ref.numpy().reshape(-1), rtol=Y_RTOL, atol=Y_ATOL)
+    y_tc = MaskedForward(g, lower(arch), [q], precision="fp32")(act, s)[:, 0].cpu().numpy()
+    np.testing.assert_allclose(y_tc, y, rtol=Y_RTOL, atol=Y_ATOL)
+    v = C.c_int32(-1)
+    _lib.check(lib.xpgnn_get_option(b"dense_simt", C.byref(v)))
+    assert v.value == 0
+
+
 def test_wlm_fit_matches_closed_form(lib):
     """Fit kernels vs the oracle's torch-autograd port on random data, both target layouts."""
     from bikg_graph_explainability_public_b200 import _lib
