@@ -1337,6 +1337,8 @@ struct CLayout {
   int32_t *long_rows, *n_long;
   int32_t *long_list, *n_long_list;
   int long_cap;  // entries per slot segment of long_list
+  int32_t *item_row, *item_slice, *row_item0, *n_items;  // sliced hub rows of layer 0 (compact_l0.cu)
+  float2* slice_scratch;
   int32_t* rows_packed;
   float* rs_packed;
   int32_t* ccol;
@@ -1371,6 +1373,11 @@ static CLayout compact_carve(const xpgnn_plan_t* p, void* ws, int64_t cap, int t
   c.counters = b.take<int32_t>(32);
   c.long_rows = b.take<int32_t>(E / kLongRow + 1);
   c.n_long = b.take<int32_t>(1);
+  c.item_row = b.take<int32_t>(l0_long_items_max(E));
+  c.item_slice = b.take<int32_t>(l0_long_items_max(E));
+  c.row_item0 = b.take<int32_t>(E / kLongRow + 2);
+  c.n_items = b.take<int32_t>(1);
+  c.slice_scratch = b.take<float2>(l0_long_items_max(E) * (h0 / 64 + 1) * 1024);
   c.long_cap = (int)(E / kLongCompact + 1);
   c.long_list = b.take<int32_t>((int64_t)tile * c.long_cap);
   c.n_long_list = b.take<int32_t>(32);
@@ -1510,13 +1517,17 @@ int forward_compact(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32
   const bool dyn_sched = !knobs().sched_static;
   XP_CHECK(cudaMemsetAsync(lay.keys + (int64_t)tile * N, 0, sizeof(unsigned long long), st));
   // hub rows get CTA-per-row variants of the row-per-warp kernels
-  int n_long = 0;
-  XP_CHECK(cudaMemsetAsync(lay.counters, 0, 16 * sizeof(int32_t), st));  // later zeroed per tile by compact_tilemap_kernel
+  int n_long = 0, n_l0_items = 0;
+  XP_CHECK(cudaMemsetAsync(lay.counters, 0, 32 * sizeof(int32_t), st));  // later zeroed per tile by compact_tilemap_kernel
   XP_CHECK(cudaMemsetAsync(lay.n_long, 0, sizeof(int32_t), st));
   XP_LAUNCH(find_long_rows_kernel, (int)ceil_div(N, 256), 256, 0, st, R0.rowptr, N, kLongRow, lay.long_rows, lay.n_long);
+  // layer 0: hub rows in slices of kL0Slice in-edges, one CTA each (compact_l0.cu)
+  if (build_l0_long_items(R0.rowptr, lay.long_rows, lay.n_long, lay.item_row, lay.item_slice, lay.row_item0, lay.n_items, st)) return 1;
   XP_CHECK(cudaMemcpyAsync(&n_long, lay.n_long, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  XP_CHECK(cudaMemcpyAsync(&n_l0_items, lay.n_items, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   XP_CHECK(cudaStreamSynchronize(st));
   if (!knobs().long_rows) n_long = 0;
+  const bool l0_slices = knobs().l0_slices != 0 && p->layers_host[0].h_out / 64 <= 4;
 
   const int w_first = s0 / 32, w_last = (s0 + n_s - 1) / 32;
   const int grid_rows = (int)std::min<int64_t>(std::max<int64_t>(ceil_div(N, 8), 1), (int64_t)kNumSMs * 8);
@@ -1580,7 +1591,10 @@ int forward_compact(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32
           if (act16) r.out_chunk_stride = cstride16;
           if (launch_l0_rows(r, sg, act16, N, st)) return 1;
           if (n_long > 0) {
-            if (launch_l0_long_rows(r, sg, act16, n_long, st)) return 1;
+            if (l0_slices) {
+              r.item_row = lay.item_row; r.item_slice = lay.item_slice; r.row_item0 = lay.row_item0; r.slice_scratch = lay.slice_scratch;
+            }
+            if (launch_l0_long_rows(r, sg, act16, n_long, st, n_l0_items)) return 1;
           }
         } else if (l == 0) {  // transform-first: gather the coalition-invariant Z
           s.n_chunks = L.h_out / cw;

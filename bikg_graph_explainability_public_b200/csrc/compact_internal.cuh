@@ -49,7 +49,16 @@ struct L0RowsArgs {
   const int32_t* rows;       // optional row list (pruned mode of the tile path): row i of the launch is rows[i], i < n_list
   int n_list;
   unsigned long long* dbg;   // XPGNN_L0_DBG: cycle counters of warp pair 0 of CTA 0 (diagnostics only)
+  // LONG launch, optional: hub rows cut into slices of kL0Slice in-edges, one CTA per slice (an 82 K-in-edge row of an R-MAT
+  // graph kept one CTA busy for ~2 ms per tile while the rest of the GPU had finished).  Item i = slice item_slice[i] of hub row
+  // long_rows[item_row[i]]; the items of row r are row_item0[r] .. row_item0[r + 1] - 1.  A row with several slices leaves
+  // its partial accumulators in slice_scratch and l0_long_reduce_kernel adds them in slice order and runs the epilogue.
+  const int32_t* item_row;
+  const int32_t* item_slice;
+  const int32_t* row_item0;
+  float2* slice_scratch;     // [item][column block][32 accumulators][32 lanes]
 };
+constexpr int kL0Slice = 4096;  // in-edges of a hub-row slice
 
 constexpr int kLongRow = 1024;    // in-edges above which a destination row is processed by a whole CTA
 constexpr int kLongCompact = 256; // active in-edges above which a compact row is processed by a whole CTA (SpMM)
@@ -112,8 +121,13 @@ int launch_cspmm_bulk(const CspmmArgs& a, int variant, cudaStream_t st);
 // ---- launchers of compact_l0.cu (return non-zero on a CUDA error, like every launch helper of the engine) ----
 // rows that are not hub rows: warp specialised by default (XPGNN_L0_WS selects the variant)
 int launch_l0_rows(const L0RowsArgs& r, bool sigmoid, bool out16, int n_rows, cudaStream_t st);
-// hub rows (r.long_rows, more than r.long_threshold in-edges): one CTA per row
-int launch_l0_long_rows(const L0RowsArgs& r, bool sigmoid, bool out16, int n_long, cudaStream_t st);
+// hub rows (r.long_rows, more than r.long_threshold in-edges): one CTA per row, or per slice when r.item_row is set
+// (n_items = number of slices over all hub rows)
+int launch_l0_long_rows(const L0RowsArgs& r, bool sigmoid, bool out16, int n_long, cudaStream_t st, int n_items = 0);
+// slices of the hub rows (graph property: once per forward call); *n_items_dev = number of items
+int build_l0_long_items(const int32_t* rowptr, const int32_t* long_rows, const int32_t* n_long_dev, int32_t* item_row, int32_t* item_slice,
+                        int32_t* row_item0, int32_t* n_items_dev, cudaStream_t st);
+inline int64_t l0_long_items_max(int64_t n_edges) { return n_edges / kLongRow + n_edges / kL0Slice + 2; }
 // all relations into one destination type in one pass (HeteroConv sum)
 int launch_l0_multi(const L0MultiArgs& a, bool sigmoid, cudaStream_t st);
 

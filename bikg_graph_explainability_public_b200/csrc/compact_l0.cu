@@ -174,11 +174,21 @@ __global__ void __launch_bounds__(256, 2) l0_rows_kernel(const L0RowsArgs a) {
   const int n_rows = a.rows ? a.n_list : a.row_hi - a.row_lo;  // row list (pruned mode) | destination range of the relation
   for (int vb = LONG ? 0 : grab_rows(a.counter, lane); vb < n_rows; vb = LONG ? n_rows : grab_rows(a.counter, lane))
   for (int vi = LONG ? 0 : vb; vi < (LONG ? 1 : min(n_rows, vb + kRowGrab)); ++vi) {
-    const int v = LONG ? a.long_rows[blockIdx.x] : (a.rows ? a.rows[vi] : a.row_lo + vi);
+    int slice = 0, n_slices = 1;  // LONG with items: this CTA sums one slice of the hub row
+    if (LONG && a.item_row) {
+      const int ri = a.item_row[blockIdx.x];
+      slice = a.item_slice[blockIdx.x];
+      n_slices = a.row_item0[ri + 1] - a.row_item0[ri];
+    }
+    const int v = LONG ? a.long_rows[a.item_row ? a.item_row[blockIdx.x] : blockIdx.x] : (a.rows ? a.rows[vi] : a.row_lo + vi);
     const uint32_t av = a.act[(int64_t)v * a.W + a.w] & live;
     if (!av) continue;  // LONG: the same row for the whole CTA, so every warp leaves together
     const int n_slots = __popc(av), nq = (n_slots + 3) >> 2;
-    const int e0 = a.rowptr[v], e1 = a.rowptr[v + 1];
+    int e0 = a.rowptr[v], e1 = a.rowptr[v + 1];
+    if (LONG && a.item_row) {
+      e0 += slice * kL0Slice;
+      e1 = min(e1, e0 + kL0Slice);
+    }
     if (!LONG && a.long_threshold > 0 && e1 - e0 > a.long_threshold) continue;  // hub row: left to the LONG launch
     const bool short_row = !LONG && e1 - e0 <= 32;
     const float sc_v = a.scale[(int64_t)v * 32 + lane];
@@ -230,6 +240,12 @@ __global__ void __launch_bounds__(256, 2) l0_rows_kernel(const L0RowsArgs a) {
         }
         __syncthreads();
         if (wib != 0) continue;
+        if (n_slices > 1) {  // partial sums of this slice: l0_long_reduce_kernel finishes the row
+          float2* sc = a.slice_scratch + ((int64_t)blockIdx.x * ncb + cb) * 1024;
+#pragma unroll
+          for (int k = 0; k < 32; ++k) sc[k * 32 + lane] = acc[k];
+          continue;
+        }
       }
       float2 self, add;
       l0_epilogue_operands(a, v, cb, lane, gcn, self, add);
@@ -1096,11 +1112,94 @@ int launch_l0_rows(const L0RowsArgs& r, bool sigmoid, bool out16, int n_rows, cu
   return 0;
 }
 
-int launch_l0_long_rows(const L0RowsArgs& r, bool sigmoid, bool out16, int n_long, cudaStream_t st) {
+// hub rows cut into slices: adds the slices' partial accumulators in slice order (deterministic) and runs the row's epilogue.
+// One CTA per hub row, warp cb = column block cb; rows with a single slice were finished by l0_rows_kernel<., LONG> itself.
+template <bool SIGMOID, bool OUT16>
+__global__ void __launch_bounds__(128) l0_long_reduce_kernel(const L0RowsArgs a) {
+  const int lane = threadIdx.x & 31, cb = threadIdx.x >> 5, ncb = a.h0 / 64, ri = blockIdx.x;
+  const int i0 = a.row_item0[ri], n_slices = a.row_item0[ri + 1] - i0;
+  if (n_slices <= 1 || cb >= ncb) return;
+  const uint32_t live = (a.nb == 32 ? 0xffffffffu : ((1u << a.nb) - 1u)) << a.b0;
+  const int v = a.long_rows[ri];
+  const uint32_t av = a.act[(int64_t)v * a.W + a.w] & live;
+  if (!av) return;
+  const bool gcn = a.kind == XPGNN_CONV_GCN;
+  const float lower = a.act_fn == XPGNN_ACT_RELU ? 0.0f : -INFINITY;
+  float2 acc[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) acc[k] = make_float2(0.f, 0.f);
+  for (int sl = 0; sl < n_slices; ++sl) {
+    const float2* sc = a.slice_scratch + ((int64_t)(i0 + sl) * ncb + cb) * 1024;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const float2 p = sc[k * 32 + lane];
+      acc[k].x += p.x; acc[k].y += p.y;
+    }
+  }
+  const float sc_v = a.scale[(int64_t)v * 32 + lane];
+  float2 self, add;
+  l0_epilogue_operands(a, v, cb, lane, gcn, self, add);
+  l0_epilogue<SIGMOID, OUT16>(a, v, av, __popc(av), cb, lane, sc_v, gcn, lower, acc, self, add);
+}
+
+// items of the sliced hub-row launch: one CTA, chunks of 256 rows with a running offset
+__global__ void __launch_bounds__(256) l0_long_items_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ long_rows,
+                                                            const int32_t* __restrict__ n_long_dev, int32_t* __restrict__ item_row,
+                                                            int32_t* __restrict__ item_slice, int32_t* __restrict__ row_item0,
+                                                            int32_t* __restrict__ n_items_dev) {
+  __shared__ int s_scan[256];
+  __shared__ int s_carry;
+  const int n_long = *n_long_dev;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n_long; base += 256) {
+    const int i = base + threadIdx.x;
+    int ns = 0;
+    if (i < n_long) {
+      const int v = long_rows[i];
+      ns = (rowptr[v + 1] - rowptr[v] + kL0Slice - 1) / kL0Slice;
+    }
+    s_scan[threadIdx.x] = ns;
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {
+      const int y = threadIdx.x >= o ? s_scan[threadIdx.x - o] : 0;
+      __syncthreads();
+      s_scan[threadIdx.x] += y;
+      __syncthreads();
+    }
+    const int off = s_carry + s_scan[threadIdx.x] - ns;
+    if (i < n_long) {
+      row_item0[i] = off;
+      for (int sl = 0; sl < ns; ++sl) { item_row[off + sl] = i; item_slice[off + sl] = sl; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 255) s_carry += s_scan[255];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { row_item0[n_long] = s_carry; *n_items_dev = s_carry; }
+}
+
+int build_l0_long_items(const int32_t* rowptr, const int32_t* long_rows, const int32_t* n_long_dev, int32_t* item_row, int32_t* item_slice,
+                        int32_t* row_item0, int32_t* n_items_dev, cudaStream_t st) {
+  XP_LAUNCH(l0_long_items_kernel, 1, 256, 0, st, rowptr, long_rows, n_long_dev, item_row, item_slice, row_item0, n_items_dev);
+  return 0;
+}
+
+int launch_l0_long_rows(const L0RowsArgs& r, bool sigmoid, bool out16, int n_long, cudaStream_t st, int n_items) {
   void (*k)(const L0RowsArgs) = out16 ? (sigmoid ? l0_rows_kernel<true, true, true> : l0_rows_kernel<false, true, true>)
                                       : (sigmoid ? l0_rows_kernel<true, true, false> : l0_rows_kernel<false, true, false>);
   XP_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kL0SmemBytes));
-  XP_LAUNCH(k, n_long, 256, kL0SmemBytes, st, r);
+  if (!r.item_row) {
+    XP_LAUNCH(k, n_long, 256, kL0SmemBytes, st, r);
+    return 0;
+  }
+  XP_REQUIRE(r.h0 / 64 <= 4, "sliced hub rows: at most 4 column blocks");
+  if (n_items > 0) XP_LAUNCH(k, n_items, 256, kL0SmemBytes, st, r);
+  if (n_items > n_long) {  // some row has several slices
+    void (*kr)(const L0RowsArgs) = out16 ? (sigmoid ? l0_long_reduce_kernel<true, true> : l0_long_reduce_kernel<false, true>)
+                                         : (sigmoid ? l0_long_reduce_kernel<true, false> : l0_long_reduce_kernel<false, false>);
+    XP_LAUNCH(kr, n_long, 128, 0, st, r);
+  }
   return 0;
 }
 

@@ -541,6 +541,8 @@ struct Layout {
   float* hub_partial = nullptr;  // sliced hub rows of tiny launches (prune)
   int32_t* l0_counter = nullptr; // row counter of the layer-0 row kernel (prune)
   int32_t* l0_long = nullptr;    // hub rows among the layer-0 row list (prune)
+  int32_t *l0_item_row = nullptr, *l0_item_slice = nullptr, *l0_row_item0 = nullptr;  // their slices (compact_l0.cu)
+  float2* l0_slice_scratch = nullptr;
   int64_t bytes = 0;
 };
 
@@ -609,6 +611,13 @@ static Layout carve(const xpgnn_plan_t* p, void* ws, int64_t cap, int tile, cons
     lay.hub_partial = b.take<float>((int64_t)kHubRows * kHubSlices * 32 * std::max(hmax, kmax));
     lay.l0_counter = b.take<int32_t>(64);
     lay.l0_long = b.take<int32_t>(N);
+    if (p->n_layers > 0 && p->layers_host[0].n_rel == 1) {  // sliced hub rows of the pruned layer 0 (homogeneous stacks)
+      const int64_t e0 = std::max(p->layers_host[0].rel_host[0].n_edges, 1), items = l0_long_items_max(e0);
+      lay.l0_item_row = b.take<int32_t>(items);
+      lay.l0_item_slice = b.take<int32_t>(items);
+      lay.l0_row_item0 = b.take<int32_t>(e0 / kLongRowTile + 2);
+      lay.l0_slice_scratch = b.take<float2>(items * (p->layers_host[0].h_out / 64 + 1) * 1024);
+    }
   }
   lay.bytes = (b.off + 255) & ~255ll;
   return lay;
@@ -727,12 +736,19 @@ int xpgnn_forward(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32_t
   const bool prune_l0 = prune_l0_env && p->prune && NL > 1 && L0.n_rel == 1 && L0.rel_host[0].src_lo == 0 && L0.rel_host[0].src_hi == N &&
                         L0.rel_host[0].dst_lo == 0 && L0.rel_host[0].dst_hi == N && L0.h_out % 64 == 0 &&
                         (int64_t)N * L0.h_out < (int64_t(1) << 31) && n_rows[0] > n_rows[1];
-  int32_t n_long0 = 0;
+  int32_t n_long0 = 0, n_items0 = 0;
+  const bool l0_slices = knobs().l0_slices != 0 && lay.l0_item_row != nullptr && L0.h_out / 64 <= 4 && kLongRowTile == kLongRow;
   if (prune_l0 && max_deg[umap[0][0]] > kLongRowTile) {
     XP_CHECK(cudaMemsetAsync(lay.l0_counter + 1, 0, sizeof(int32_t), st));
     XP_LAUNCH(long_rows_of_list_kernel, (int)ceil_div(n_rows[0], 256), 256, 0, st, lay.rows[0], n_rows[0], L0.rel_host[0].rowptr, kLongRowTile,
               lay.l0_long, lay.l0_counter + 1);
     XP_CHECK(cudaMemcpyAsync(&n_long0, lay.l0_counter + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (l0_slices) {
+      if (build_l0_long_items(L0.rel_host[0].rowptr, lay.l0_long, lay.l0_counter + 1, lay.l0_item_row, lay.l0_item_slice, lay.l0_row_item0,
+                              lay.l0_counter + 2, st))
+        return 1;
+      XP_CHECK(cudaMemcpyAsync(&n_items0, lay.l0_counter + 2, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    }
     XP_CHECK(cudaStreamSynchronize(st));
   }
   XP_REQUIRE(L0.h_in == p->f_in, "layer 0 input width != feature width");
@@ -868,8 +884,12 @@ int xpgnn_forward(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32_t
               }
               if (n_long0 > 0) {  // hub rows of the list: one CTA per row
                 a.long_rows = lay.l0_long;
+                if (l0_slices) {
+                  a.item_row = lay.l0_item_row; a.item_slice = lay.l0_item_slice; a.row_item0 = lay.l0_row_item0;
+                  a.slice_scratch = lay.l0_slice_scratch;
+                }
                 ProfScope ps(PROF_SPMM_INVARIANT, st);
-                if (launch_l0_long_rows(a, L.act == XPGNN_ACT_SIGMOID, false, n_long0, st)) return 1;
+                if (launch_l0_long_rows(a, L.act == XPGNN_ACT_SIGMOID, false, n_long0, st, n_items0)) return 1;
               }
               s.rows = lay.rows[1]; s.n_rows = n_rows[1];  // every slot of the rows the next layer reads as its own
             }

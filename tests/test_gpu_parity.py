@@ -341,7 +341,8 @@ def test_compact_path_matches_oracle(kind, hidden, env, lib, knobs):
 @pytest.mark.parametrize("kind", ["gcn", "sage"])
 def test_compact_path_hub_rows(kind, lib, knobs):
     """Destination rows above the long-row threshold (1024 in-edges) are processed by whole CTAs in the compact
-    path (hub rows of power-law graphs); same predictions as the oracle and as the tile path."""
+    path (hub rows of power-law graphs), in layer 0 cut into slices of 4096 in-edges whose partial sums a second kernel
+    adds in slice order; same predictions as the oracle and as the tile path."""
     from bikg_graph_explainability_public_b200.engine import GraphSpec, MaskedForward
     from bikg_graph_explainability_public_b200.lowering import lower
     from oracle.xpgnn_oracle import kernel_output
@@ -350,7 +351,7 @@ def test_compact_path_hub_rows(kind, lib, knobs):
     g = torch.Generator().manual_seed(5)
     n = x.shape[0]
     hubs = [q, 7, 1234]
-    extra = [torch.stack([torch.randint(0, n, (k,), generator=g), torch.full((k,), h)]) for h, k in zip(hubs, (2500, 3000, 1100))]
+    extra = [torch.stack([torch.randint(0, n, (k,), generator=g), torch.full((k,), h)]) for h, k in zip(hubs, (9000, 4100, 1100))]  # 3, 2 and 1 slices of 4096 in-edges in layer 0
     ei = torch.cat([ei] + extra, 1)
     s = mask.shape[0]
     mask[2, q] = True
@@ -369,6 +370,9 @@ def test_compact_path_hub_rows(kind, lib, knobs):
     np.testing.assert_allclose(yp[:, 0], y[:, 0], rtol=2e-5, atol=1e-6)
     yp2 = MaskedForward(gs, lower(arch), [q], prune=True, hop=hop)(act, s).cpu().numpy()
     np.testing.assert_array_equal(yp2, yp)  # slices are added in a fixed order
+    np.testing.assert_array_equal(MaskedForward(gs, lower(arch), [q, 7])(act, s).cpu().numpy(), y)  # slices add in a fixed order
+    knobs(l0_slices=0)   # one CTA per hub row
+    np.testing.assert_allclose(MaskedForward(gs, lower(arch), [q, 7])(act, s).cpu().numpy(), y, rtol=2e-5, atol=1e-6)
     knobs(long_rows=0)   # hub rows through the row-per-warp kernels
     np.testing.assert_allclose(MaskedForward(gs, lower(arch), [q, 7])(act, s).cpu().numpy(), y, rtol=2e-5, atol=1e-6)
     knobs(compact=0)
