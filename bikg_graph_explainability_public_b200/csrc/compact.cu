@@ -1995,7 +1995,7 @@ int forward_compact_hetero(const xpgnn_plan_t* p, const uint32_t* act, int32_t W
 
   // hub rows per relation CSR
   for (auto& c : lay.csr) {
-    XP_CHECK(cudaMemsetAsync(c.counters, 0, 16 * sizeof(int32_t), st));
+    XP_CHECK(cudaMemsetAsync(c.counters, 0, 32 * sizeof(int32_t), st));
     XP_CHECK(cudaMemsetAsync(c.n_long_dev, 0, sizeof(int32_t), st));
     XP_LAUNCH(find_long_rows_kernel, (int)ceil_div(N, 256), 256, 0, st, c.rowptr, N, kLongRow, c.long_rows, c.n_long_dev);
   }
