@@ -519,7 +519,7 @@ __global__ void __launch_bounds__(256) cspmm_long_kernel(const CspmmArgs a) {
 // Sums run in list order (self first), so results do not depend on the schedule.  Rows with more than long_cnt active
 // in-edges stay with cspmm_long_kernel.
 // ------------------------------------------------------------------------------------------
-constexpr int kSegCap = 320;     // stream positions staged per round; a longer row is summed alone, chunk by chunk
+constexpr int kSegCap = 512;     // stream positions staged per round; a longer row is summed alone, chunk by chunk.  (320 until the r02 profile: a C3 block of 32 rows has 352 +- 18 positions, so nearly every block took a second round for its last 3 rows.)
 constexpr int kSegTileLd = 36;   // floats per tile row (144 B: 16-byte aligned, consecutive rows 4 banks apart)
 constexpr int kSegRowwise = 24;  // blocks whose longest row has at most this many entries are staged row by row
 static_assert(kSegCap % 32 == 0 && kSegCap >= 128, "staging buffer: whole 32-position steps, room for the 4 x 128-byte partial sums");
@@ -670,11 +670,19 @@ __global__ void __launch_bounds__(128, OCC) cspmm_seg_kernel(const CspmmArgs a) 
       const bool in_round = lane >= r_lo && lane < r_hi;
       // ---- stage the stream words of this round: source id | last << 31 ----
       if (n_max <= kSegRowwise) {  // short rows: lane = row
-        if (in_round && n_l > 0) {
-          int o = a_l;
-          if (gcn) ids[o++] = (uint32_t)v_l | (n_l == 1 ? 0x80000000u : 0u);
-          const int ne = n_l - (gcn ? 1 : 0);
-          for (int k = 0; k < ne; ++k) ids[o + k] = (uint32_t)__ldg(cc + e_l + k) | (k == ne - 1 ? 0x80000000u : 0u);
+        // 8 list entries per step, loads first: the r02 source-level profile showed 7 % of the warp stalls in a one-entry-per-
+        // iteration form of this loop (load -> use -> store, one exposed round trip per entry)
+        const bool have = in_round && n_l > 0;
+        const int ne = have ? n_l - (gcn ? 1 : 0) : 0;
+        int o = a_l;
+        if (have && gcn) ids[o++] = (uint32_t)v_l | (n_l == 1 ? 0x80000000u : 0u);
+        for (int k0 = 0; k0 < n_max; k0 += 8) {  // n_max: warp-uniform bound
+          uint32_t t8[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) t8[j] = k0 + j < ne ? (uint32_t)__ldg(cc + e_l + k0 + j) : 0u;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (k0 + j < ne) ids[o + k0 + j] = t8[j] | (k0 + j == ne - 1 ? 0x80000000u : 0u);
         }
       } else {                     // lane = stream position, its row by binary search over the row ends
         for (int i = lane; i < len; i += 32) {
