@@ -540,7 +540,7 @@ __device__ __forceinline__ void seg_add(float4& acc, const float4& x) {
       : "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w));
 }
 
-template <int D, int OCC>
+template <int D, int OCC, int PF>  // PF: list entries per row prefetched during the previous block's epilogue (0: none)
 __global__ void __launch_bounds__(128, OCC) cspmm_seg_kernel(const CspmmArgs a) {
   constexpr int WARPS = 4;
   __shared__ int s_start[33];
@@ -565,10 +565,12 @@ __global__ void __launch_bounds__(128, OCC) cspmm_seg_kernel(const CspmmArgs a) 
 
   // ---- two-deep item pipeline: item n is processed while the metadata loads of n + 1 and the counter fetch of n + 2 fly ----
   int t_cur = 0;
-  auto grab = [&]() {
+  // the counter fetch of block n + 2 is ISSUED a block before its value is needed and broadcast only then (r02 source-level
+  // profile: 4.6 % of the warp stalls sat in a fetch-and-broadcast at this point -- one atomic round trip per block)
+  auto grab_raw = [&]() {
     int it = 0;
     if (lane == 0) it = atomicAdd(a.counter, 1);
-    return __shfl_sync(0xffffffffu, it, 0);
+    return it;  // valid in lane 0
   };
   // decodes the item into s_next and issues the loads of its row ids / list offsets
   auto load_meta = [&](int item, int& v, uint32_t& e, uint32_t& f) {
@@ -589,11 +591,26 @@ __global__ void __launch_bounds__(128, OCC) cspmm_seg_kernel(const CspmmArgs a) 
       f = __ldcs(rp + 1);
     }
   };
-  int item1 = grab();
+  int item1 = __shfl_sync(0xffffffffu, grab_raw(), 0);
   int v1;
   uint32_t e1, f1;
   load_meta(item1, v1, e1, f1);
-  int item2 = grab();
+  int raw2 = grab_raw();
+  // The first kPf list entries of every row of the NEXT block are loaded into registers while the current block runs its
+  // epilogue (the gather queue's registers are free then; the next block's row offsets arrived long ago): the staging of
+  // a block then stores them without waiting -- its two exposed list round trips were 7 % of the warp stalls (r02 profile).
+  constexpr int kPf = PF;
+  uint32_t pf[kPf > 0 ? kPf : 1];
+  auto prefetch_ids = [&]() {  // (v1, e1, f1) and s_next describe the block whose staging comes next
+    if (kPf == 0) return;
+    __syncwarp();
+    const uint32_t cnt_n = f1 - e1;
+    const bool mine_n = item1 < total && v1 >= 0 && !(a.long_cnt > 0 && cnt_n > (uint32_t)a.long_cnt);
+    const int32_t* cc_n = a.ccol + (item1 < total ? a.slot_base[s_next[warp][0]] : 0ll) + e1;
+#pragma unroll
+    for (int j = 0; j < kPf; ++j) pf[j] = (mine_n && (uint32_t)j < cnt_n) ? (uint32_t)__ldg(cc_n + j) : 0u;
+  };
+  prefetch_ids();
 
   while (item1 < total) {
     __syncwarp();
@@ -619,9 +636,9 @@ __global__ void __launch_bounds__(128, OCC) cspmm_seg_kernel(const CspmmArgs a) 
       s_sc[warp][lane] = gcn ? gcn_dinv(cnt_l) : (cnt_l ? 1.0f / (float)cnt_l : 0.0f);
       nA = __shfl_sync(0xffffffffu, a_end, 31);
       nonempty = __ballot_sync(0xffffffffu, n_l > 0);  // the tile holds the sums of these rows, in row order
-      item1 = item2;
+      item1 = __shfl_sync(0xffffffffu, raw2, 0);
       load_meta(item1, v1, e1, f1);   // consumed at the top of the next iteration
-      item2 = grab();
+      raw2 = grab_raw();
     }
     const int n_max = __reduce_max_sync(0xffffffffu, n_l);
     __syncwarp();
@@ -676,7 +693,10 @@ __global__ void __launch_bounds__(128, OCC) cspmm_seg_kernel(const CspmmArgs a) 
         const int ne = have ? n_l - (gcn ? 1 : 0) : 0;
         int o = a_l;
         if (have && gcn) ids[o++] = (uint32_t)v_l | (n_l == 1 ? 0x80000000u : 0u);
-        for (int k0 = 0; k0 < n_max; k0 += 8) {  // n_max: warp-uniform bound
+#pragma unroll
+        for (int j = 0; j < kPf; ++j)  // entries prefetched during the previous block's epilogue
+          if (j < ne) ids[o + j] = pf[j] | (j == ne - 1 ? 0x80000000u : 0u);
+        for (int k0 = kPf; k0 < n_max; k0 += 8) {  // the rest (rows longer than kPf entries); n_max: warp-uniform bound
           uint32_t t8[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) t8[j] = k0 + j < ne ? (uint32_t)__ldg(cc + e_l + k0 + j) : 0u;
@@ -762,6 +782,7 @@ __global__ void __launch_bounds__(128, OCC) cspmm_seg_kernel(const CspmmArgs a) 
       __syncwarp();
       r_lo = r_hi;
     }
+    prefetch_ids();  // list entries of the next block: in flight during the epilogue and the next block's scan
     // ---- epilogue: scale and write the 32 rows, 4 rows per instruction ----
     float* out_c = a.out + (int64_t)t * a.out_s_stride + (int64_t)c * a.out_chunk_stride + sub * 4;
 #pragma unroll
@@ -1430,11 +1451,15 @@ static int launch_cspmm(const CspmmArgs& a, int cw, cudaStream_t st) {
       if (a.long_cnt > 0) XP_LAUNCH((cspmm_long_kernel<32, false>), kNumSMs * 8, 256, 0, st, a);
       return 0;
     }
-    if (seg >= 16) k = cspmm_seg_kernel<16, 4>;       // 16 warps / SM x 16 gathers in flight per lane (128 registers)
-    else if (seg >= 12) k = cspmm_seg_kernel<12, 5>;  // 20 warps / SM x 12
-    else if (seg >= 8) k = socc == 8 ? cspmm_seg_kernel<8, 8> : (socc == 7 ? cspmm_seg_kernel<8, 7> : cspmm_seg_kernel<8, 6>);
-    else if (seg >= 6) k = socc == 6 ? cspmm_seg_kernel<6, 6> : (socc == 7 ? cspmm_seg_kernel<6, 7> : cspmm_seg_kernel<6, 8>);
-    else k = socc == 10 ? cspmm_seg_kernel<4, 10> : cspmm_seg_kernel<4, 8>;
+    const int pf = knobs().seg_pf;
+    if (seg >= 16) k = cspmm_seg_kernel<16, 4, 0>;       // 16 warps / SM x 16 gathers in flight per lane (128 registers)
+    else if (seg >= 12) k = cspmm_seg_kernel<12, 5, 0>;  // 20 warps / SM x 12
+    else if (seg >= 8) {
+      if (socc == 8) k = cspmm_seg_kernel<8, 8, 0>;
+      else if (socc == 7) k = cspmm_seg_kernel<8, 7, 0>;
+      else k = pf >= 16 ? cspmm_seg_kernel<8, 6, 16> : (pf >= 12 ? cspmm_seg_kernel<8, 6, 12> : (pf >= 8 ? cspmm_seg_kernel<8, 6, 8> : cspmm_seg_kernel<8, 6, 0>));
+    } else if (seg >= 6) k = socc == 6 ? cspmm_seg_kernel<6, 6, 0> : (socc == 7 ? cspmm_seg_kernel<6, 7, 0> : cspmm_seg_kernel<6, 8, 0>);
+    else k = socc == 10 ? cspmm_seg_kernel<4, 10, 0> : (pf >= 8 ? cspmm_seg_kernel<4, 8, 8> : cspmm_seg_kernel<4, 8, 0>);
     int per_sm = 0;
     XP_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, 128, 0));
     ProfScope ps(a.prof_cat > 0 ? a.prof_cat : PROF_SPMM_TILE, st);
