@@ -243,6 +243,14 @@ __global__ void __launch_bounds__(32 * (1 + P + C), MINB) cspmm_bulk_kernel(cons
 #endif
     unsigned long long t_w0 = 0, t_w1 = 0, t_f = 0, n_st = 0;
     const long long t_begin = clock64();
+    uint32_t done_n = 0;  // this warp has arrived on dempty of every item below done_n
+    auto finish_items = [&](uint32_t upto) {
+      while (done_n < upto) {
+        __syncwarp();
+        if (lane == 0) bg_arrive(&S.dempty[done_n % kBgDesc]);
+        ++done_n;
+      }
+    };
     // 0: produced the next stage of this warp | 1: the next item's descriptor is not there yet (only when !may_block) | 2: end
     auto f_next = [&](int& id, uint32_t& g, uint32_t& item_no, bool may_block) -> int {
       for (;;) {
@@ -279,14 +287,10 @@ __global__ void __launch_bounds__(32 * (1 + P + C), MINB) cspmm_bulk_kernel(cons
         }
         ++fn;
         f_nst = -1;
-      }
-    };
-    uint32_t done_n = 0;  // this warp has arrived on dempty of every item below done_n
-    auto finish_items = [&](uint32_t upto) {
-      while (done_n < upto) {
-        __syncwarp();
-        if (lane == 0) bg_arrive(&S.dempty[done_n % kBgDesc]);
-        ++done_n;
+        // may_block means the queue is empty: every stage this warp owns in the items before the cursor has been issued.
+        // Let go of them NOW -- a warp that owns no stage in kBgDesc consecutive (short) items would otherwise wait for a
+        // descriptor the scheduler can only publish after this warp's arrival on an item it is still holding.
+        if (may_block) finish_items(fn);
       }
     };
     auto issue = [&](int id, uint32_t g, uint32_t item_no) {
