@@ -699,7 +699,7 @@ __global__ void __launch_bounds__(128, OCC) cspmm_seg_kernel(const CspmmArgs a) 
         for (int k0 = kPf; k0 < n_max; k0 += 8) {  // the rest (rows longer than kPf entries); n_max: warp-uniform bound
           uint32_t t8[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) t8[j] = k0 + j < ne ? (uint32_t)__ldg(cc + e_l + k0 + j) : 0u;
+          for (int j = 0; j < 8; ++j) t8[j] = k0 + j < ne ? (uint32_t)__ldg(cc + e_l + k0 + j) : 0u;  // (ld.global.cs here: 9.72 vs 9.50 ms -- the entries of a row share sectors in L1)
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             if (k0 + j < ne) ids[o + k0 + j] = t8[j] | (k0 + j == ne - 1 ? 0x80000000u : 0u);
