@@ -300,10 +300,28 @@ __device__ __forceinline__ void ws_mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void ws_cp_async_arrive(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(ws_u32(bar)) : "memory");
 }
+// > 0: waiting warps suspend inside mbarrier.try_wait (suspend-time hint in ns, woken by the hardware when the phase completes)
+// instead of polling with nanosleep -- the r02 source-level profile counted 38 % of the warp-specialised layer-0 kernel's executed
+// instructions in the polling loops (option l0_wait_ns)
+__constant__ int g_l0_wait_hint_ns = 0;
 template <int SLEEP_NS>
 __device__ __forceinline__ void ws_mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = ws_u32(bar);
   uint32_t done = 0;
+  const uint32_t hint = (uint32_t)g_l0_wait_hint_ns;
+  if (hint > 0) {
+    for (uint32_t spin = 0; !done; ++spin) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(addr), "r"(parity), "r"(hint)
+          : "memory");
+      if (spin > (1u << 22)) __trap();
+    }
+    return;
+  }
   for (uint32_t spin = 0; !done; ++spin) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -1057,6 +1075,14 @@ __global__ void __launch_bounds__(256, 2) l0_multi_kernel(const L0MultiArgs a) {
 // layer-0 row kernel over the rows that are not hub rows: warp specialised by default, XPGNN_L0_WS=0 selects the
 // one-warp-per-row kernel (same arithmetic, same order: bit-identical)
 int launch_l0_rows(const L0RowsArgs& r, bool sigmoid, bool out16, int n_rows, cudaStream_t st) {
+  {
+    static int hint_set = 0;  // value of g_l0_wait_hint_ns on the device
+    const int want = knobs().l0_wait_ns;
+    if (want != hint_set) {
+      XP_CHECK(cudaMemcpyToSymbolAsync(g_l0_wait_hint_ns, &want, sizeof(int), 0, cudaMemcpyHostToDevice, st));
+      hint_set = want;
+    }
+  }
   // l0_ws option: 3 = 1 with the Z pieces moved by TMA bulk copies (UBLKCP) instead of cp.async;
   // 1 (default) warp specialised, column-block tiling; 2 warp specialised, slot x column tiling (widths % 128 == 0:
   // 40 % fewer shared-memory wavefronts and fewer cycles, but a lower clock under the power cap -- 6.2 against 5.3 ms at C3);

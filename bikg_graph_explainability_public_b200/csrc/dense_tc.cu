@@ -35,11 +35,30 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 #define XP_EXP(a, bit) false
 #endif
 __constant__ int g_backoff_after = 16;  // failed polls before a waiting thread starts sleeping (XPGNN_DENSE_BACKOFF)
+// > 0: waiting threads SUSPEND inside mbarrier.try_wait (suspend-time hint in ns; the hardware wakes them when the phase
+// completes) instead of polling -- the r02 source-level profile counted 60 % of this kernel's executed instructions in the
+// polling loop of its 21 waiting warps, every poll a shared-memory operation in a kernel bound by the shared-memory pipe
+// (option dense_wait_ns)
+__constant__ int g_wait_hint_ns = 0;
 
 template <bool BACKOFF = true>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
+  const uint32_t hint = (uint32_t)g_wait_hint_ns;
+  if (hint > 0) {
+    for (uint32_t spin = 0; !done; ++spin) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(addr), "r"(parity), "r"(hint)
+          : "memory");
+      if (spin > (1u << 22)) __trap();
+    }
+    return;
+  }
   for (uint32_t spin = 0; !done; ++spin) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -570,6 +589,14 @@ int launch_dense_tc(const DenseArgs& d_in, int mode, cudaStream_t st) {
 #else
   d.exp_flags = 0;
 #endif
+  {
+    static int hint_set = 0;  // value of g_wait_hint_ns on the device (one device per process)
+    const int want = knobs().dense_wait_ns;
+    if (want != hint_set) {
+      XP_CHECK(cudaMemcpyToSymbolAsync(g_wait_hint_ns, &want, sizeof(int), 0, cudaMemcpyHostToDevice, st));
+      hint_set = want;
+    }
+  }
   XP_REQUIRE(tc_eligible(d, mode), "shape not eligible for the tensor-core dense path");
   const int n_pad = (d.n_out + 15) / 16 * 16;
   uint32_t cols = 32;

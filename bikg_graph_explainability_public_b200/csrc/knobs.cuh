@@ -32,6 +32,9 @@ struct Knobs {
   int l0_ws = 3;           // XPGNN_L0_WS: 0 one warp per row | 1 warp specialised, cp.async staging | 2 slot x column tiling |
                            // 3 (default) = 1 with the Z pieces staged by TMA bulk copies (UBLKCP): same arithmetic, bit-identical;
                            // measured at C3 4.91 vs 4.93 ms per tile, R-MAT 10.27 vs 10.32 (profiles/r02_summary.md)
+  int l0_wait_ns = 2000;    // XPGNN_L0_WAIT_NS: the same for the warp-specialised layer-0 kernel
+  int dense_wait_ns = 2000;  // XPGNN_DENSE_WAIT_NS: > 0 = waiting warps of dense_tc suspend inside mbarrier.try_wait (hint in ns) instead of polling
+                           // (0 = poll + nanosleep; measured 3.94 -> 3.89 ms per C3 tile launch, layer 0 4.96 -> 4.95)
   int dense_simt = 0;      // XPGNN_DENSE=simt: exact fp32 FMA transforms instead of 3xTF32 tensor-core products
   int prune_l0 = 1;        // XPGNN_PRUNE_L0
   int fused = 0;           // XPGNN_FUSED
