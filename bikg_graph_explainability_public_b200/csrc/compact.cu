@@ -733,11 +733,14 @@ __global__ void __launch_bounds__(128, OCC) cspmm_seg_kernel(const CspmmArgs a) 
       }
       // ---- cut at row boundaries into four pieces of ~len / 4 positions: piece g starts at the first non-empty row that
       // begins at or after position g * per; its sums go to consecutive tile rows ----
+      // (the boundary is the row start NEAREST to g * per: taking the first start at or after it made piece 0 about one row
+      // longer and piece 3 one row shorter than the mean, and the warp runs as long as its longest piece)
       const int per = (len + 3) >> 2;
+      const int half = (len / max(r_hi - r_lo, 1)) >> 1;  // half an average row
       int q = 0, q1 = len, trow = __popc(nonempty & ((1u << r_lo) - 1u));
 #pragma unroll
       for (int g = 1; g < 4; ++g) {
-        const uint32_t m = __ballot_sync(0xffffffffu, in_round && n_l > 0 && a_l >= g * per);
+        const uint32_t m = __ballot_sync(0xffffffffu, in_round && n_l > 0 && a_l + half >= g * per);
         const int first = m ? __ffs(m) - 1 : 32;
         const int start = m ? __shfl_sync(0xffffffffu, a_l, first & 31) : len;
         if (grp == g) { q = start; trow = __popc(nonempty & ((1u << (first & 31)) - 1u)); }
