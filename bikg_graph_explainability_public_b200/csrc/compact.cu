@@ -521,6 +521,9 @@ __global__ void __launch_bounds__(256) cspmm_long_kernel(const CspmmArgs a) {
 // ------------------------------------------------------------------------------------------
 constexpr int kSegCap = 512;     // stream positions staged per round; a longer row is summed alone, chunk by chunk.  (320 until the r02 profile: a C3 block of 32 rows has 352 +- 18 positions, so nearly every block took a second round for its last 3 rows.)
 constexpr int kSegTileLd = 36;   // floats per tile row (144 B: 16-byte aligned, consecutive rows 4 banks apart)
+// Shared memory per CTA: 28.9 KB -> six CTAs need the 196 KB carve-out, the L1 keeps 60 KB.  Measured (r02 calls 48 - 50): with the
+// 228 KB carve-out (28 KB of L1: forced, or needed by 7 CTAs per SM) the kernel takes 14.0 - 14.3 ms per C3 tile instead of 9.4; with
+// 25.9 KB per CTA (448 positions, unpadded tile rows: 164 KB carve-out, 92 KB of L1) it takes the same 9.4 ms (R-MAT: 12.7 vs 12.4).
 constexpr int kSegRowwise = 24;  // blocks whose longest row has at most this many entries are staged row by row
 static_assert(kSegCap % 32 == 0 && kSegCap >= 128, "staging buffer: whole 32-position steps, room for the 4 x 128-byte partial sums");
 
@@ -1470,12 +1473,15 @@ static int launch_cspmm(const CspmmArgs& a, int cw, cudaStream_t st) {
     const int pf = knobs().seg_pf;
     if (seg >= 16) k = cspmm_seg_kernel<16, 4, 0>;       // 16 warps / SM x 16 gathers in flight per lane (128 registers)
     else if (seg >= 12) k = cspmm_seg_kernel<12, 5, 0>;  // 20 warps / SM x 12
+    else if (seg == 7) k = cspmm_seg_kernel<7, 7, 0>;     // 28 warps / SM x 7 gathers in flight (73 registers at most)
     else if (seg >= 8) {
       if (socc == 8) k = cspmm_seg_kernel<8, 8, 0>;
       else if (socc == 7) k = cspmm_seg_kernel<8, 7, 0>;
       else k = pf >= 16 ? cspmm_seg_kernel<8, 6, 16> : (pf >= 12 ? cspmm_seg_kernel<8, 6, 12> : (pf >= 8 ? cspmm_seg_kernel<8, 6, 8> : cspmm_seg_kernel<8, 6, 0>));
     } else if (seg >= 6) k = socc == 6 ? cspmm_seg_kernel<6, 6, 0> : (socc == 7 ? cspmm_seg_kernel<6, 7, 0> : cspmm_seg_kernel<6, 8, 0>);
     else k = socc == 10 ? cspmm_seg_kernel<4, 10, 0> : (pf >= 8 ? cspmm_seg_kernel<4, 8, 8> : cspmm_seg_kernel<4, 8, 0>);
+    if (knobs().seg_carve > 0)  // experiment: shared-memory carve-out in percent (what is left of the 256 KB is L1)
+      XP_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, knobs().seg_carve));
     int per_sm = 0;
     XP_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, 128, 0));
     ProfScope ps(a.prof_cat > 0 ? a.prof_cat : PROF_SPMM_TILE, st);

@@ -18,6 +18,7 @@ struct Knobs {
   int seg_skew = 0;        // XPGNN_SEG_SKEW: the `seg` value used instead when the graph has hub rows (skewed degrees: many short rows
                            // next to the long ones; R-MAT C3: 13.2 ms per tile with 4 in flight at 8 CTAs against 13.8 with 8 at 6); 0: same as seg
   int seg_pf = 0;          // XPGNN_SEG_PF: list entries per row the segmented kernel prefetches into registers during the previous block's epilogue (0 | 8 | 12 | 16); measured slower (register spills: 9.58 / 10.22 / 10.82 vs 9.50 ms per C3 tile)
+  int seg_carve = 0;       // XPGNN_SEG_CARVE: > 0 = preferred shared-memory carve-out of the segmented kernel in percent (experiment: L1 size)
   int seg_occ = 0;         // XPGNN_SEG_OCC: 0 default CTAs / SM of the chosen segmented variant
   int seg_tma = 0;         // XPGNN_SEG_TMA: 1 = a small TMA gather4 kernel (compact_bulk.cu) runs next to the segmented SpMM on a second stream;
                            // both take blocks from the same in-order counter (bit-identical results)
