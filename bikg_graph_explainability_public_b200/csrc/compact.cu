@@ -519,11 +519,13 @@ __global__ void __launch_bounds__(256) cspmm_long_kernel(const CspmmArgs a) {
 // Sums run in list order (self first), so results do not depend on the schedule.  Rows with more than long_cnt active
 // in-edges stay with cspmm_long_kernel.
 // ------------------------------------------------------------------------------------------
-constexpr int kSegCap = 512;     // stream positions staged per round; a longer row is summed alone, chunk by chunk.  (320 until the r02 profile: a C3 block of 32 rows has 352 +- 18 positions, so nearly every block took a second round for its last 3 rows.)
-constexpr int kSegTileLd = 36;   // floats per tile row (144 B: 16-byte aligned, consecutive rows 4 banks apart)
-// Shared memory per CTA: 28.9 KB -> six CTAs need the 196 KB carve-out, the L1 keeps 60 KB.  Measured (r02 calls 48 - 50): with the
-// 228 KB carve-out (28 KB of L1: forced, or needed by 7 CTAs per SM) the kernel takes 14.0 - 14.3 ms per C3 tile instead of 9.4; with
-// 25.9 KB per CTA (448 positions, unpadded tile rows: 164 KB carve-out, 92 KB of L1) it takes the same 9.4 ms (R-MAT: 12.7 vs 12.4).
+constexpr int kSegCap = 448;     // stream positions staged per round; a longer row is summed alone, chunk by chunk.  (320 until the r02 profile: a C3 block of 32 rows has 352 +- 18 positions, so nearly every block took a second round for its last 3 rows.)
+constexpr int kSegTileLd = 32;   // floats per tile row (128 B; a warp-wide 16-byte access is 4 wavefronts with or without padding)
+// Shared memory per CTA: 25.9 KB (448 staged positions, unpadded tile rows), so that SEVEN CTAs fit the 196 KB carve-out and the L1
+// keeps 60 KB.  Measured (r02 calls 48 - 51, ms per C3 tile): with 28.9 KB per CTA (512 positions, padded rows) 7 CTAs need the
+// 228 KB carve-out and the kernel takes 14.0 with 28 KB of L1 (6 CTAs, forced 228 KB: 14.3; 6 CTAs at 196 KB: 9.4); with 25.9 KB:
+// 8 in flight x 6 CTAs 9.42, 7 x 7 CTAs 9.08 (shipped, option seg = 7), 8 x 7 CTAs 9.11, 6 x 7 CTAs 9.20.  (Every earlier
+// occupancy sweep of this kernel above 6 CTAs per SM had silently run with 28 KB of L1.)
 constexpr int kSegRowwise = 24;  // blocks whose longest row has at most this many entries are staged row by row
 static_assert(kSegCap % 32 == 0 && kSegCap >= 128, "staging buffer: whole 32-position steps, room for the 4 x 128-byte partial sums");
 
@@ -1450,7 +1452,7 @@ static int launch_cspmm(const CspmmArgs& a, int cw, cudaStream_t st) {
   void (*k)(const CspmmArgs);
   // aggregate-first layers >= 1 (plain scaled sums over 32-float chunks): the segmented kernel
   int seg = knobs().seg;  // 0: row-lockstep kernel | 4 / 6 / 8: gathers in flight per lane
-  if (seg == 8 && a.long_cnt > 0 && knobs().seg_skew > 0) seg = knobs().seg_skew;  // hub rows in the graph: skewed degrees
+  if ((seg == 7 || seg == 8) && a.long_cnt > 0 && knobs().seg_skew > 0) seg = knobs().seg_skew;  // hub rows in the graph: skewed degrees
   if (seg > 0 && cw == 32 && a.counter && !a.wgt && !a.addend && !a.bias && !a.layer0 && !a.prescale && a.act_fn == XPGNN_ACT_NONE) {
     const int socc = knobs().seg_occ;
     if (seg >= 200) {  // warp-specialised TMA bulk-copy variant (compact_bulk.cu): seg = 200 + 100 * mode + ring stages (16 | 32): 216 / 232 bulk copies, 316 / 332 cp.async.cg, 432 cp.async.ca, 516 / 532 TMA gather4

@@ -13,8 +13,8 @@ struct Knobs {
   int cw = 32;             // XPGNN_CW: 32 | 16 floats per activation chunk
   int l0_lists = 0;        // XPGNN_L0=lists: list-driven layer 0 instead of the row-outer kernels
   int occ = 8;             // XPGNN_OCC: CTAs / SM of the row-lockstep SpMM
-  int seg = 8;             // XPGNN_SEG: 0 row-lockstep SpMM | 4 / 6 / 8 segmented SpMM with that many gathers in flight per lane
-                           // (measured at C3: 8 at 6 CTAs / SM 11.07 ms per tile, 6 at 6: 11.41, 4 at 8: 13.64, row-lockstep 11.59)
+  int seg = 7;             // XPGNN_SEG: 0 row-lockstep SpMM | 4 / 6 / 7 / 8 / 12 / 16 segmented SpMM with that many gathers in flight per lane
+                           // (C3, ms per tile: 7 at 7 CTAs / SM 9.08, 8 at 7: 9.11, 8 at 6: 9.42, 6 at 7: 9.20, 12 at 5: 10.0, row-lockstep 11.7)
   int seg_skew = 0;        // XPGNN_SEG_SKEW: the `seg` value used instead when the graph has hub rows (skewed degrees: many short rows
                            // next to the long ones; R-MAT C3: 13.2 ms per tile with 4 in flight at 8 CTAs against 13.8 with 8 at 6); 0: same as seg
   int seg_pf = 0;          // XPGNN_SEG_PF: list entries per row the segmented kernel prefetches into registers during the previous block's epilogue (0 | 8 | 12 | 16); measured slower (register spills: 9.58 / 10.22 / 10.82 vs 9.50 ms per C3 tile)

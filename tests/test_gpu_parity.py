@@ -380,7 +380,7 @@ def test_compact_path_hub_rows(kind, lib, knobs):
 
 
 @pytest.mark.parametrize("kind", ["gcn", "sage"])
-@pytest.mark.parametrize("seg", ["0", "4", "6", "8", "12", "16", "116", "124", "216", "232", "316", "332", "432", "516", "532", "8t"])
+@pytest.mark.parametrize("seg", ["0", "4", "6", "7", "8", "12", "16", "116", "124", "216", "232", "316", "332", "432", "516", "532", "8t"])
 def test_segmented_spmm_variants(kind, seg, lib, knobs):
     """Layers >= 1 through the segmented SpMM (cspmm_seg_kernel: a warp sums the gather stream of a 32-row block in four
     pieces cut at row boundaries) with 4 .. 16 gathers in flight per lane, through its shared-memory ring variant (116 / 124:
