@@ -7,7 +7,8 @@
 // per-lane cp.async.bulk (UBLKCP takes its operands from uniform registers, so a warp issues its 32 copies one by one)
 // 9 - 15; the TMA gather4 form (UTMALDG.2D.GATHER4: 4 rows of a 2-D tensor map per instruction, row indices in registers)
 // 29.7 = 8.4 TB/s per GPU, TMA-unit bound; plain LDG.128 > 40 (11.3 TB/s in tools/gather_probe.cu).  Alone, this kernel is
-// therefore SLOWER than the register-queue kernel (cspmm_seg_kernel, compact.cu): 19 - 36 ms per C3 tile against 11.1.
+// therefore SLOWER than the register-queue kernel (cspmm_seg_kernel, compact.cu): 19 - 36 ms per C3 tile against 11.1 when it was
+// measured (8.9 now).
 // But the register-queue kernel is not fabric bound either -- it is short of registers for gathers in flight -- and the TMA
 // unit is idle while it runs.  MODE 3 (gather4) is built to run NEXT TO it: both kernels take 32-row blocks from the same
 // in-order work counter, this one with few warps and no register queue, so the TMA unit adds its bytes per cycle to those of
