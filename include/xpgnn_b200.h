@@ -36,9 +36,10 @@ int64_t xpgnn_launch_count(void);
 /* Engine options.  Every option selects between implementations of the same function (kernel variant, occupancy, path
  * selection); none changes what is computed beyond floating-point summation order.  The XPGNN_<NAME> environment
  * variables only seed the defaults and are read ONCE, at the first use of the library; afterwards an option changes
- * only through this call.  Names (csrc/knobs.cuh): compact, compact_hetero, cw, l0_lists, occ, seg, seg_occ, l2_stream,
- * l2_gather, sched_static, long_rows, occ16, l0_multi, l1_multi, l0_ws, dense_simt (1: exact fp32 FMA transforms
- * instead of the 3xTF32 tensor-core products of the fp32 plan), prune_l0, fused, fused_sb.
+ * only through this call.  Names (csrc/knobs.cuh): compact, compact_hetero, cw, l0_lists, occ, seg, seg_occ, seg_skew, seg_tma,
+ * seg_pf, seg_carve, l2_stream, l2_gather, sched_static, long_rows, l0_slices, occ16, l0_multi, l1_multi, l0_ws, l0_wait_ns,
+ * dense_wait_ns, dense_simt (1: exact fp32 FMA transforms instead of the 3xTF32 tensor-core products of the fp32 plan),
+ * prune_l0, fused, fused_sb.
  * The reference has no counterpart (its arch call is a black box, model.py:104-112). */
 int xpgnn_set_option(const char* name, int32_t value);
 int xpgnn_get_option(const char* name, int32_t* value);
