@@ -99,6 +99,14 @@ __global__ void __launch_bounds__(256) compact_degree_long_kernel(const int32_t*
   if (t >= 0 && t < nb) keys[(int64_t)t * n_rows + (v - row_lo)] = ((av >> lane) & 1u) ? ((1ull << kKeyShift) | (unsigned long long)cnt) : 0ull;
 }
 
+// word `w` of every node's coalition bits as a dense array: the kernels of a tile gather act[u] once per edge, and with W = 128 words
+// per node (the 4096-coalition job) every such gather touched its own 32-byte sector of a 512 MB matrix; the column is 4 MB
+// (r02: masked degree 1.02 -> per-tile cost of the W = 4 case)
+__global__ void __launch_bounds__(256) extract_word_kernel(const uint32_t* __restrict__ act, int W, int w, int N, uint32_t* __restrict__ out) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < N) out[v] = act[(int64_t)v * W + w];
+}
+
 // destination rows with more than `threshold` in-edges (a property of the graph: found once per forward call)
 __global__ void __launch_bounds__(256) find_long_rows_kernel(const int32_t* __restrict__ rowptr, int N, int threshold,
                                                              int32_t* __restrict__ list, int32_t* __restrict__ count) {
@@ -1389,6 +1397,7 @@ struct CLayout {
   int32_t *long_list, *n_long_list;
   int long_cap;  // entries per slot segment of long_list
   int32_t *item_row, *item_slice, *row_item0, *n_items;  // sliced hub rows of layer 0 (compact_l0.cu)
+  uint32_t* act_word;  // [N] the tile's word of the coalition bits (extract_word_kernel)
   float2* slice_scratch;
   int32_t* rows_packed;
   float* rs_packed;
@@ -1428,6 +1437,7 @@ static CLayout compact_carve(const xpgnn_plan_t* p, void* ws, int64_t cap, int t
   c.item_slice = b.take<int32_t>(l0_long_items_max(E));
   c.row_item0 = b.take<int32_t>(E / kLongRow + 2);
   c.n_items = b.take<int32_t>(1);
+  c.act_word = b.take<uint32_t>(N);
   c.slice_scratch = b.take<float2>(l0_long_items_max(E) * (h0 / 64 + 1) * 1024);
   c.long_cap = (int)(E / kLongCompact + 1);
   c.long_list = b.take<int32_t>((int64_t)tile * c.long_cap);
@@ -1531,7 +1541,7 @@ static int launch_cspmm(const CspmmArgs& a, int cw, cudaStream_t st) {
   return 0;
 }
 
-int forward_compact(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32_t s0, int32_t n_s, float* y, void* workspace,
+int forward_compact(const xpgnn_plan_t* p, const uint32_t* act_in, int32_t W_in, int32_t s0, int32_t n_s, float* y, void* workspace,
                     int64_t workspace_bytes, int64_t* stats, cudaStream_t st, int dense_prec) {
   const int N = p->n_nodes, NL = p->n_layers;
   const xpgnn_relation_t& R0 = p->layers_host[0].rel_host[0];
@@ -1589,8 +1599,15 @@ int forward_compact(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32
 
   const int w_first = s0 / 32, w_last = (s0 + n_s - 1) / 32;
   const int grid_rows = (int)std::min<int64_t>(std::max<int64_t>(ceil_div(N, 8), 1), (int64_t)kNumSMs * 8);
-  for (int w = w_first; w <= w_last; ++w) {
-    const int bits_in_word = std::min(32, s0 + n_s - w * 32);
+  for (int w_idx = w_first; w_idx <= w_last; ++w_idx) {
+    const int bits_in_word = std::min(32, s0 + n_s - w_idx * 32);
+    // the kernels of this word read the bits as act[v * W + w]: from the caller's matrix, or from the 4 MB column of this word
+    const uint32_t* act = act_in;
+    int W = W_in, w = w_idx;
+    if (W_in > 1 && knobs().act_column) {
+      XP_LAUNCH(extract_word_kernel, (int)ceil_div(N, 256), 256, 0, st, act_in, W_in, w_idx, (int)N, lay.act_word);
+      act = lay.act_word; W = 1; w = 0;
+    }
     for (int b0 = 0; b0 < bits_in_word; b0 += tile) {
       const int nb = std::min(tile, bits_in_word - b0);
       // ---- per-tile compaction ----
@@ -1726,7 +1743,7 @@ int forward_compact(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32
       }
       h.in = cur; h.in_s_stride = hstride; h.in_chunk_stride = cstride; h.dim0 = p->layers_host[NL - 1].h_out; h.cw = cw; h.cw_lg = cw_lg; h.in16 = act16; if (act16) h.in_chunk_stride = cstride16;
       h.query = p->query; h.n_query = p->n_query; h.out_col = p->out_col;
-      h.y = y + ((int64_t)(w * 32 + b0) - s0) * p->n_query;
+      h.y = y + ((int64_t)(w_idx * 32 + b0) - s0) * p->n_query;
       h.act = act; h.W = W; h.w = w; h.b0 = b0;
       {
         ProfScope ps(PROF_HEAD, st);

@@ -25,6 +25,7 @@ struct Knobs {
   int l2_stream = 1;       // XPGNN_L2_STREAM / XPGNN_L2_GATHER: L2 eviction priority of streamed / gathered accesses
   int l2_gather = 0;
   int sched_static = 0;    // XPGNN_SCHED=static: static round-robin instead of the in-order work counter
+  int act_column = 1;      // XPGNN_ACT_COLUMN: the compact path copies the tile's word of the coalition matrix into a dense [N] array first
   int l0_slices = 1;       // XPGNN_L0_SLICES: hub rows of layer 0 cut into 4096-in-edge slices, one CTA each (0: one CTA per hub row)
   int long_rows = 1;       // XPGNN_LONG=0: hub rows through the row-per-warp kernels
   int occ16 = 8;           // XPGNN_OCC16
