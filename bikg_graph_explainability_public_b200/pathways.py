@@ -87,17 +87,20 @@ class Pathways:
         ``np.intersect1d(..., return_indices=True)`` yields, pathways.py:84-96,131-134), plus their names.  The lists are in
         ascending index order instead of lexicographic name order: ``Mask.mask_generator`` sorts them numerically in place
         before anything reads them (masks.py:323), and the community mean does not depend on the order.
-        One name -> first-index dict, then per community a C-level key-view intersection and a numeric sort (measured
-        against a vectorised numpy / pandas join over all members: 0.35 s vs 0.6 s at 564 k names / 1 M members -- the
-        cost is hashing scattered Python strings either way)."""
+        One name -> first-index dict, then per community one pass of C-level dict lookups and a numeric sort (measured
+        against a vectorised numpy / pandas join over all members: 0.6 s at 564 k names / 1 M members -- the cost is hashing
+        scattered Python strings either way)."""
         first = _first_index(names)
-        keys = first.keys()
-        lookup = first.__getitem__
+        lookup = first.get
         inds, kept = [], []
         for community, cname in zip(self.communities, self.community_names):
-            common = keys & set(_as_str(community))
-            if common:
-                inds.append(sorted(map(lookup, common)))
+            # one C-level pass of dict lookups over the members (absent names give None), duplicates collapse in the set of
+            # indices.  (Same 0.42 s as "set(members) & keys, then look the survivors up" at 564 k names / 1 M members: the time
+            # is the 1 M probes into a hash table that does not fit the caches.)
+            found = set(map(lookup, _as_str(community)))
+            found.discard(None)
+            if found:
+                inds.append(sorted(found))
                 kept.append(cname)
         return inds, kept
 
