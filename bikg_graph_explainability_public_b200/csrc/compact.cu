@@ -1438,7 +1438,7 @@ static CLayout compact_carve(const xpgnn_plan_t* p, void* ws, int64_t cap, int t
   c.row_item0 = b.take<int32_t>(E / kLongRow + 2);
   c.n_items = b.take<int32_t>(1);
   c.act_word = b.take<uint32_t>(N);
-  c.slice_scratch = b.take<float2>(l0_long_items_max(E) * (h0 / 64 + 1) * 1024);
+  c.slice_scratch = b.take<float2>(l0_slice_scratch_items(E) * (h0 / 64 + 1) * 1024);
   c.long_cap = (int)(E / kLongCompact + 1);
   c.long_list = b.take<int32_t>((int64_t)tile * c.long_cap);
   c.n_long_list = b.take<int32_t>(32);
@@ -1595,7 +1595,8 @@ int forward_compact(const xpgnn_plan_t* p, const uint32_t* act_in, int32_t W_in,
   XP_CHECK(cudaMemcpyAsync(&n_l0_items, lay.n_items, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   XP_CHECK(cudaStreamSynchronize(st));
   if (!knobs().long_rows) n_long = 0;
-  const bool l0_slices = knobs().l0_slices != 0 && p->layers_host[0].h_out / 64 <= 4;
+  const bool l0_slices = knobs().l0_slices != 0 && p->layers_host[0].h_out / 64 <= 4 &&
+                         n_l0_items <= l0_slice_scratch_items(std::max(R0.n_edges, 1));
 
   const int w_first = s0 / 32, w_last = (s0 + n_s - 1) / 32;
   const int grid_rows = (int)std::min<int64_t>(std::max<int64_t>(ceil_div(N, 8), 1), (int64_t)kNumSMs * 8);

@@ -1,6 +1,8 @@
 // Shared by the compact-path translation units: compact.cu (per-tile compaction, list-driven SpMM, head, the two
 // drivers) and compact_l0.cu (layer-0 row kernels).
 #pragma once
+#include <algorithm>
+
 #include "engine_internal.cuh"
 
 namespace xpgnn {
@@ -128,6 +130,11 @@ int launch_l0_long_rows(const L0RowsArgs& r, bool sigmoid, bool out16, int n_lon
 int build_l0_long_items(const int32_t* rowptr, const int32_t* long_rows, const int32_t* n_long_dev, int32_t* item_row, int32_t* item_slice,
                         int32_t* row_item0, int32_t* n_items_dev, cudaStream_t st);
 inline int64_t l0_long_items_max(int64_t n_edges) { return n_edges / kLongRow + n_edges / kL0Slice + 2; }
+// The scratch of the sliced hub rows (8 KB per item and column block) is sized for at most this many items -- the worst case of
+// l0_long_items_max would be 2.9 GB at 100 M edges for graphs that may have no hub row at all; a call with more items runs its
+// hub rows unsliced (one CTA per row)
+constexpr int64_t kL0SliceScratchItems = 16384;
+inline int64_t l0_slice_scratch_items(int64_t n_edges) { return std::min<int64_t>(l0_long_items_max(n_edges), kL0SliceScratchItems); }
 // all relations into one destination type in one pass (HeteroConv sum)
 int launch_l0_multi(const L0MultiArgs& a, bool sigmoid, cudaStream_t st);
 

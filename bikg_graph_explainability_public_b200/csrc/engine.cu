@@ -616,7 +616,7 @@ static Layout carve(const xpgnn_plan_t* p, void* ws, int64_t cap, int tile, cons
       lay.l0_item_row = b.take<int32_t>(items);
       lay.l0_item_slice = b.take<int32_t>(items);
       lay.l0_row_item0 = b.take<int32_t>(e0 / kLongRowTile + 2);
-      lay.l0_slice_scratch = b.take<float2>(items * (p->layers_host[0].h_out / 64 + 1) * 1024);
+      lay.l0_slice_scratch = b.take<float2>(l0_slice_scratch_items(e0) * (p->layers_host[0].h_out / 64 + 1) * 1024);
     }
   }
   lay.bytes = (b.off + 255) & ~255ll;
@@ -884,7 +884,7 @@ int xpgnn_forward(const xpgnn_plan_t* p, const uint32_t* act, int32_t W, int32_t
               }
               if (n_long0 > 0) {  // hub rows of the list: one CTA per row
                 a.long_rows = lay.l0_long;
-                if (l0_slices) {
+                if (l0_slices && n_items0 <= l0_slice_scratch_items(std::max(R.n_edges, 1))) {
                   a.item_row = lay.l0_item_row; a.item_slice = lay.l0_item_slice; a.row_item0 = lay.l0_row_item0;
                   a.slice_scratch = lay.l0_slice_scratch;
                 }
